@@ -1,0 +1,475 @@
+// trainer.cu — the fused IA2C episode: rollout, critic phase, actor phase (N agents, E envs).
+//
+// Replaces the episode body of ia2c.py:62-129:
+//   rollout        ia2c.py:72-102   (env step, 2N actor forwards + samples, belief updates, trajectory)
+//   critic phase   ia2c.py:104-114  (+ CriticNetwork.batch_update, ac_nets.py:62-72)
+//   actor phase    ia2c.py:116-129  (+ ActorNetwork.batch_update, ac_nets.py:112-119, no zero_grad)
+// generalised from 2 to N agents as specified in DESIGN.md ("Org-N"; identical to the reference at N=2).
+//
+// Kernels in this file
+//   rollout_step_kernel   one time step for all envs: Org transition from act[t-1] (counts reduced by
+//                         warp shuffles, agents in lanes), observation, every agent's actor forward +
+//                         sample -> act[t], true-partner mode.  Per-agent actor weights staged in smem.
+//   critic_grad_kernel    per (agent, row): Q(obs), Q(next_obs), TD target with gradient through both
+//                         passes (residual gradient), closed-form backward accumulated in
+//                         registers, block-reduced to partials (fixed order).
+//   actor_grad_kernel     per (agent, row): advantage from the updated critic (2 critic forwards), actor
+//                         forward, Categorical log-prob/entropy loss, closed-form backward, partials.
+//   reduce_adam_kernel    sums the partials, writes grad (+loss), and applies Adam (actor: accumulating
+//                         gradient buffer).
+// The belief update between steps is belief_pairs_kernel (belief.cu).
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace ia2c {
+namespace {
+
+constexpr int F = IA2C_OBS_FEATURES, A = IA2C_AGENT_ACTIONS, J = IA2C_JOINT_ACTIONS;
+constexpr int kRolloutThreads = 128;
+constexpr int kGradThreads = 128;
+constexpr float kEpsClamp = 1.1920928955078125e-07f;
+
+__device__ __forceinline__ int mode3(int c0, int c1, int c2) {
+    int best = 0, bc = c0;
+    if (c1 > bc) { best = 1; bc = c1; }
+    if (c2 > bc) { best = 2; }
+    return best;
+}
+
+// joint index for agent i: lower agent index is the high digit, partner (i+1) mod N
+__device__ __forceinline__ int joint_index(int i, int n, int own, int other) {
+    return (i < (i + 1) % n) ? own * A + other : other * A + own;
+}
+
+// ------------------------------------------------------------------------------------------------
+struct StepArgs {
+    ia2c_episode_desc d;
+    int t;
+    int G;   // lanes per env (power of two, min(32, pow2ceil(N)))
+};
+
+__device__ __forceinline__ uint32_t pack_count(int a) { return a == 0 ? 1u : (a == 1 ? (1u << 10) : (1u << 20)); }
+
+__global__ void __launch_bounds__(kRolloutThreads) rollout_step_kernel(StepArgs S) {
+    extern __shared__ float w_actor[];  // [N][105]
+    const ia2c_episode_desc& d = S.d;
+    const int N = d.N, G = S.G, t = S.t;
+    for (int i = threadIdx.x; i < N * kActorP; i += blockDim.x) w_actor[i] = d.actor_params[i];
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31;
+    const int sub = lane & (G - 1);
+    const int epw = 32 / G;                                        // envs per warp
+    const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t e = warp_global * epw + (lane / G);
+    const bool live = e < d.E;                                     // whole group shares this
+    const int64_t E = d.E;
+
+    // ---- environment: reset at t == 0, otherwise one Org step from act[t-1]
+    int prev_cls = 1, cur_cls = 1;
+    if (t > 0) {
+        uint32_t packed = 0;
+        if (live) {
+            const uint8_t* a_prev = d.act + ((int64_t)(t - 1) * E + e) * N;
+            for (int i = sub; i < N; i += G) packed += pack_count(a_prev[i]);
+        }
+        for (int off = G >> 1; off > 0; off >>= 1) packed += __shfl_xor_sync(0xffffffffu, packed, off);
+        if (live && sub == 0) {
+            const int s = d.env_state[e];
+            int s2;
+            double base;
+            org_transition(s, packed & 1023, (packed >> 10) & 1023, (packed >> 20) & 1023, N, s2, base);
+            double r = org_reward(base, d.env_hist[e]);
+            prev_cls = d.env_cls[2 * e + 1];
+            cur_cls = org_obs_class(s2);
+            d.reward[(int64_t)(t - 1) * E + e] = (float)r;         // float32(r) as stored by ia2c.py:99
+            d.ep_return[e] += r;                                   // fp64, in step order (ia2c.py:102)
+            if (d.state_trace) d.state_trace[(int64_t)(t - 1) * E + e] = s2;
+            if (d.reward_f64) d.reward_f64[(int64_t)(t - 1) * E + e] = r;
+            int el = d.env_elapsed[e] + 1;
+            if (d.max_episode_steps > 0 && el >= d.max_episode_steps) {  // same-step autoreset (Q14)
+                s2 = 2; r = 0.0; prev_cls = 1; cur_cls = 1; el = 0;
+            }
+            d.env_state[e] = s2;
+            d.env_hist[e] = r;
+            d.env_elapsed[e] = el;
+            *reinterpret_cast<uchar2*>(d.env_cls + 2 * e) = make_uchar2((unsigned char)prev_cls, (unsigned char)cur_cls);
+        }
+    } else if (live && sub == 0) {
+        d.env_state[e] = 2;
+        d.env_hist[e] = 0.0;
+        d.env_elapsed[e] = 0;
+        d.ep_return[e] = 0.0;
+        *reinterpret_cast<uchar2*>(d.env_cls + 2 * e) = make_uchar2(1, 1);
+    }
+    const int leader = lane & ~(G - 1);
+    prev_cls = __shfl_sync(0xffffffffu, prev_cls, leader);
+    cur_cls = __shfl_sync(0xffffffffu, cur_cls, leader);
+    float x[F];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        x[k] = (k == prev_cls) ? 1.f : 0.f;
+        x[3 + k] = (k == cur_cls) ? 1.f : 0.f;
+    }
+    if (live && sub < F) {
+        for (int k = sub; k < F; k += G) d.obs[((int64_t)t * E + e) * F + k] = x[k];
+    }
+
+    // ---- every agent's actor forward + sample; agents strided over the group's lanes
+    uint8_t* act_t = d.act + ((int64_t)t * E + e) * N;
+    uint32_t packed = 0;
+    for (int i = sub; i < N; i += G) {
+        if (!live) break;
+        int a;
+        if (d.inj_actions) {
+            a = d.inj_actions[((int64_t)t * E + e) * N + i];
+        } else {
+            float h1[H], h2[H], y[A];
+            mlp_forward<F, A>(w_actor + i * kActorP, x, h1, h2, y);
+            softmax_inplace<A>(y);
+            const float u = d.inj_u_action ? d.inj_u_action[((int64_t)t * E + e) * N + i]
+                                           : philox_uniform_f32(d.seed, kStreamAction, d.episode, (uint32_t)t,
+                                                                (uint64_t)((d.env_offset + e) * N + i));
+            a = sample_inverse_cdf<A>(y, u);
+        }
+        act_t[i] = (uint8_t)a;
+        packed += pack_count(a);
+    }
+    for (int off = G >> 1; off > 0; off >>= 1) packed += __shfl_xor_sync(0xffffffffu, packed, off);
+    if (live) {
+        const int c0 = packed & 1023, c1 = (packed >> 10) & 1023, c2 = (packed >> 20) & 1023;
+        uint8_t* pt = d.partner_true + ((int64_t)t * E + e) * N;
+        for (int i = sub; i < N; i += G) {
+            const int a = act_t[i];  // written by this same thread above
+            pt[i] = (uint8_t)mode3(c0 - (a == 0), c1 - (a == 1), c2 - (a == 2));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void load_obs(const float* __restrict__ p, float (&x)[F]) {
+    const float2* p2 = reinterpret_cast<const float2*>(p);
+    const float2 a = __ldg(p2), b = __ldg(p2 + 1), c = __ldg(p2 + 2);
+    x[0] = a.x; x[1] = a.y; x[2] = b.x; x[3] = b.y; x[4] = c.x; x[5] = c.y;
+}
+
+// partial row layout: P gradient entries then the loss partial.
+__global__ void __launch_bounds__(kGradThreads) critic_grad_kernel(ia2c_episode_desc d, float* __restrict__ partials) {
+    constexpr int P = kCriticP;
+    __shared__ float w[P];
+    __shared__ float red[(kGradThreads / 32) * (P + 1)];
+    const int n = blockIdx.y, N = d.N;
+    for (int i = threadIdx.x; i < P; i += blockDim.x) w[i] = d.critic_params[(int64_t)n * P + i];
+    __syncthreads();
+    const int64_t E = d.E, rows = (int64_t)d.T * E;
+    const float inv_b = 1.f / (float)((int64_t)d.T * d.E_total);
+    float g[P + 1];
+#pragma unroll
+    for (int i = 0; i <= P; ++i) g[i] = 0.f;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x) {
+        float x[F], xn[F], h1[H], h2[H], q[J], h1n[H], h2n[H], qn[J];
+        load_obs(d.obs + r * F, x);
+        load_obs(d.obs + (r + E) * F, xn);                       // next_obs[t] = obs[t+1]
+        mlp_forward<F, J>(w, x, h1, h2, q);
+        mlp_forward<F, J>(w, xn, h1n, h2n, qn);
+        const int own = d.act[r * N + n], own_n = d.act[(r + E) * N + n];
+        const int jt = joint_index(n, N, own, d.partner_true[r * N + n]);            // ia2c.py:112
+        const int nja = joint_index(n, N, own_n, d.partner_pred[(r + E) * N + n]);   // ia2c.py:104-105
+        float qsel = 0.f, qnsel = 0.f;
+#pragma unroll
+        for (int o = 0; o < J; ++o) {
+            qsel = (o == jt) ? q[o] : qsel;
+            qnsel = (o == nja) ? qn[o] : qnsel;
+        }
+        const float target = d.reward[r] + d.gamma * qnsel;      // ia2c.py:110 (graph attached, Q8)
+        const float delta = target - qsel;
+        if (d.target_dump) d.target_dump[(int64_t)n * rows + r] = target;
+        g[P] = fmaf(delta, delta, g[P]);
+        const float gq = -2.f * delta * inv_b;
+        float dy[J];
+#pragma unroll
+        for (int o = 0; o < J; ++o) dy[o] = (o == jt) ? gq : 0.f;
+        mlp_backward_accum<F, J>(w, x, h1, h2, dy, g);
+        const float gqn = 2.f * d.gamma * delta * inv_b;
+#pragma unroll
+        for (int o = 0; o < J; ++o) dy[o] = (o == nja) ? gqn : 0.f;
+        mlp_backward_accum<F, J>(w, xn, h1n, h2n, dy, g);
+    }
+    block_reduce_store<P + 1>(g, red, partials + ((int64_t)n * gridDim.x + blockIdx.x) * (P + 1));
+}
+
+__global__ void __launch_bounds__(kGradThreads) actor_grad_kernel(ia2c_episode_desc d, float* __restrict__ partials) {
+    constexpr int P = kActorP, PC = kCriticP;
+    __shared__ float wc[PC];
+    __shared__ float w[P];
+    __shared__ float red[(kGradThreads / 32) * (P + 1)];
+    const int n = blockIdx.y, N = d.N;
+    for (int i = threadIdx.x; i < PC; i += blockDim.x) wc[i] = d.critic_params[(int64_t)n * PC + i];
+    for (int i = threadIdx.x; i < P; i += blockDim.x) w[i] = d.actor_params[(int64_t)n * P + i];
+    __syncthreads();
+    const int64_t E = d.E, rows = (int64_t)d.T * E;
+    const float inv_b = 1.f / (float)((int64_t)d.T * d.E_total);
+    float g[P + 1];
+#pragma unroll
+    for (int i = 0; i <= P; ++i) g[i] = 0.f;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x) {
+        float x[F], xn[F], h1[H], h2[H];
+        load_obs(d.obs + r * F, x);
+        load_obs(d.obs + (r + E) * F, xn);
+        const int own = d.act[r * N + n], own_n = d.act[(r + E) * N + n];
+        const int ja = joint_index(n, N, own, d.partner_pred[r * N + n]);            // ia2c.py:120-121
+        const int nja = joint_index(n, N, own_n, d.partner_pred[(r + E) * N + n]);
+        float adv;
+        {   // advantage from the UPDATED critic, no gradient (ia2c.py:116-127)
+            float q[J], qn[J];
+            mlp_forward<F, J>(wc, x, h1, h2, q);
+            mlp_forward<F, J>(wc, xn, h1, h2, qn);
+            float qsel = 0.f, qnsel = 0.f;
+#pragma unroll
+            for (int o = 0; o < J; ++o) {
+                qsel = (o == ja) ? q[o] : qsel;
+                qnsel = (o == nja) ? qn[o] : qnsel;
+            }
+            adv = (d.reward[r] + d.gamma * qnsel) - qsel;
+        }
+        if (d.adv_dump) d.adv_dump[(int64_t)n * rows + r] = adv;
+        float p[A];
+        mlp_forward<F, A>(w, x, h1, h2, p);
+        softmax_inplace<A>(p);
+        // Categorical(probs=p): q = p/sum(p); logit = log(clamp(q)); loss_row = adv*(-logit[a]) - beta*H
+        float s = 0.f;
+#pragma unroll
+        for (int o = 0; o < A; ++o) s += p[o];
+        float ent = 0.f, qg = 0.f, neglogp = 0.f, gq[A], qq[A];
+#pragma unroll
+        for (int o = 0; o < A; ++o) {
+            const float q = p[o] / s;
+            const bool inside = (q >= kEpsClamp) && (q <= 1.f - kEpsClamp);
+            const float logit = logf(fminf(fmaxf(q, kEpsClamp), 1.f - kEpsClamp));
+            ent -= logit * q;
+            float go = d.beta * (logit + (inside ? 1.f : 0.f));
+            if (o == own) {
+                neglogp = -logit;
+                if (inside) go -= adv / q;
+            }
+            gq[o] = go;
+            qq[o] = q;
+            qg = fmaf(q, go, qg);
+        }
+        g[P] += adv * neglogp - d.beta * ent;
+        float dy[A];
+#pragma unroll
+        for (int o = 0; o < A; ++o) dy[o] = qq[o] * (gq[o] - qg) * inv_b;   // through normalise + softmax
+        mlp_backward_accum<F, A>(w, x, h1, h2, dy, g);
+    }
+    block_reduce_store<P + 1>(g, red, partials + ((int64_t)n * gridDim.x + blockIdx.x) * (P + 1));
+}
+
+// Sum partials over blocks (fixed order) -> grad[n][0..P] (slot P = loss); optionally Adam.
+struct ReduceArgs {
+    const float* partials;
+    int n_blocks, P;
+    float* grad;            // [N, P+1]
+    float* grad_accum;      // [N, P] or null
+    float* params; float* m; float* v;
+    int32_t* step;          // [N], incremented here when apply_adam
+    float* loss_out;        // [N]
+    float loss_scale;       // 1 / (T * E_total)
+    double lr;
+    int apply_adam, from_partials;
+};
+
+__device__ __forceinline__ void adam_update(float& p, float& m, float& v, float g, int t, double lr) {
+    const double b1 = 0.9, b2 = 0.999;
+    const double bc1 = 1.0 - pow(b1, (double)t), bc2 = 1.0 - pow(b2, (double)t);
+    const float step_size = (float)(lr / bc1), bc2_sqrt = (float)sqrt(bc2);
+    const float mi = m + (g - m) * (float)(1.0 - b1);
+    const float vi = v * (float)b2 + (float)(1.0 - b2) * g * g;
+    m = mi;
+    v = vi;
+    p = p - step_size * (mi / (sqrtf(vi) / bc2_sqrt + 1e-8f));
+}
+
+__global__ void __launch_bounds__(256) reduce_adam_kernel(ReduceArgs R) {
+    const int n = blockIdx.x, P = R.P;
+    __shared__ int t_shared;
+    if (threadIdx.x == 0) t_shared = R.step[n] + 1;
+    __syncthreads();
+    const int t = t_shared;
+    for (int i = threadIdx.x; i <= P; i += blockDim.x) {
+        float s;
+        if (R.from_partials) {
+            s = 0.f;
+            const float* src = R.partials + (int64_t)n * R.n_blocks * (P + 1) + i;
+            for (int b = 0; b < R.n_blocks; ++b) s += src[(int64_t)b * (P + 1)];
+            if (i == P) s *= R.loss_scale;
+            R.grad[(int64_t)n * (P + 1) + i] = s;
+        } else {
+            s = R.grad[(int64_t)n * (P + 1) + i];
+        }
+        if (i == P) {
+            R.loss_out[n] = s;
+        } else if (R.apply_adam) {
+            const int64_t k = (int64_t)n * P + i;
+            float g = s;
+            if (R.grad_accum) {          // the reference's actor never zeroes its gradients (Q2)
+                g += R.grad_accum[k];
+                R.grad_accum[k] = g;
+            }
+            adam_update(R.params[k], R.m[k], R.v[k], g, t, R.lr);
+        }
+    }
+    __syncthreads();
+    if (R.apply_adam && threadIdx.x == 0) R.step[n] = t;
+}
+
+int grad_blocks(const ia2c_episode_desc* d) {
+    const int64_t rows = (int64_t)d->T * d->E;
+    int64_t b = (rows + kGradThreads * 2 - 1) / (kGradThreads * 2);   // ~2 rows per thread
+    const int64_t cap = std::max<int64_t>(1, (int64_t)kSMs * 8 / std::max(1, d->N));
+    b = std::min<int64_t>(b, std::max<int64_t>(cap, 8));
+    return (int)std::max<int64_t>(1, b);
+}
+
+int validate(const ia2c_episode_desc* d, const char* who) {
+    IA2C_REQUIRE(d != nullptr, "%s: null descriptor", who);
+    IA2C_REQUIRE(d->E > 0 && d->E_total >= d->E && d->T > 0 && d->T < 65535, "%s: E=%lld E_total=%lld T=%d", who,
+                 (long long)d->E, (long long)d->E_total, d->T);
+    IA2C_REQUIRE(d->N >= 2 && d->N <= 1023, "%s: N=%d outside 2..1023", who, d->N);
+    IA2C_REQUIRE(d->M >= 2 && d->M <= IA2C_MAX_MODELS, "%s: M=%d outside 2..%d", who, d->M, IA2C_MAX_MODELS);
+    IA2C_REQUIRE(d->actor_params && d->critic_params && d->obs && d->reward && d->act && d->partner_true &&
+                     d->partner_pred, "%s: null network/trajectory pointer", who);
+    return 0;
+}
+
+}  // namespace
+}  // namespace ia2c
+
+using namespace ia2c;
+
+extern "C" size_t ia2c_episode_partials_floats(const ia2c_episode_desc* d) {
+    if (!d || d->N < 1 || d->E < 1 || d->T < 1) return 0;
+    return (size_t)d->N * grad_blocks(d) * (kCriticP + 1);
+}
+
+extern "C" int ia2c_rollout(const ia2c_episode_desc* d, void* stream) {
+    if (int rc = validate(d, "ia2c_rollout")) return rc;
+    IA2C_REQUIRE(d->env_state && d->env_hist && d->env_cls && d->env_elapsed && d->ep_return && d->belief_records &&
+                     d->filter_action, "ia2c_rollout: null env/belief pointer");
+    cudaStream_t s = as_stream(stream);
+    StepArgs S;
+    S.d = *d;
+    int G = 1;
+    while (G < d->N && G < 32) G <<= 1;
+    S.G = G;
+    const int epw = 32 / G;
+    const int64_t warps = (d->E + epw - 1) / epw;
+    const int blocks = ceil_div(warps * 32, kRolloutThreads);
+    const size_t smem = (size_t)d->N * kActorP * sizeof(float);
+    if (smem > 48 * 1024) {
+        IA2C_REQUIRE(smem <= 220 * 1024, "ia2c_rollout: N=%d actor weights do not fit shared memory", d->N);
+        cudaFuncSetAttribute(rollout_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    }
+    const int64_t EN = d->E * d->N, K = d->N - 1;
+    for (int t = 0; t <= d->T; ++t) {
+        S.t = t;
+        rollout_step_kernel<<<blocks, kRolloutThreads, smem, s>>>(S);
+        if (int rc = check_launch("rollout_step_kernel")) return rc;
+        int rc = ia2c_belief_update_pairs(
+            d->belief_records, d->filter_action, d->act + (int64_t)t * EN,
+            d->inj_u_belief ? d->inj_u_belief + (int64_t)t * EN * K : nullptr,
+            d->pred_dump ? d->pred_dump + (int64_t)t * EN * K : nullptr,
+            d->belief_dump ? d->belief_dump + (int64_t)t * EN * K * d->M : nullptr,
+            d->partner_pred + (int64_t)t * EN, d->E, d->N, d->M, /*reset_prior=*/t == 0, d->seed, d->episode,
+            (uint32_t)t, d->env_offset, stream);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+static int run_reduce(const ia2c_episode_desc* d, int which, int from_partials, int apply, cudaStream_t s) {
+    ReduceArgs R;
+    R.partials = d->partials;
+    R.n_blocks = grad_blocks(d);
+    R.P = which == 0 ? kCriticP : kActorP;
+    R.grad = which == 0 ? d->critic_grad : d->actor_grad;
+    R.grad_accum = which == 0 ? nullptr : d->actor_grad_accum;
+    R.params = which == 0 ? d->critic_params : d->actor_params;
+    R.m = which == 0 ? d->critic_m : d->actor_m;
+    R.v = which == 0 ? d->critic_v : d->actor_v;
+    R.step = which == 0 ? d->critic_step : d->actor_step;
+    R.loss_out = d->loss_out + (which == 0 ? 0 : d->N);
+    R.loss_scale = 1.f / (float)((int64_t)d->T * d->E_total);
+    R.lr = which == 0 ? d->lr_critic : d->lr_actor;
+    R.apply_adam = apply;
+    R.from_partials = from_partials;
+    reduce_adam_kernel<<<d->N, 256, 0, s>>>(R);
+    return check_launch("reduce_adam_kernel");
+}
+
+static int check_update_ptrs(const ia2c_episode_desc* d, const char* who) {
+    IA2C_REQUIRE(d->partials && d->partials_floats >= ia2c_episode_partials_floats(d), "%s: partials workspace too small", who);
+    IA2C_REQUIRE(d->critic_grad && d->actor_grad && d->critic_m && d->critic_v && d->actor_m && d->actor_v &&
+                     d->actor_grad_accum && d->critic_step && d->actor_step && d->loss_out, "%s: null optimiser pointer", who);
+    return 0;
+}
+
+extern "C" int ia2c_critic_phase(const ia2c_episode_desc* d, void* stream) {
+    if (int rc = validate(d, "ia2c_critic_phase")) return rc;
+    if (int rc = check_update_ptrs(d, "ia2c_critic_phase")) return rc;
+    cudaStream_t s = as_stream(stream);
+    dim3 grid(grad_blocks(d), d->N);
+    critic_grad_kernel<<<grid, kGradThreads, 0, s>>>(*d, d->partials);
+    if (int rc = check_launch("critic_grad_kernel")) return rc;
+    return run_reduce(d, 0, 1, !(d->flags & IA2C_FLAG_SKIP_ADAM), s);
+}
+
+extern "C" int ia2c_actor_phase(const ia2c_episode_desc* d, void* stream) {
+    if (int rc = validate(d, "ia2c_actor_phase")) return rc;
+    if (int rc = check_update_ptrs(d, "ia2c_actor_phase")) return rc;
+    cudaStream_t s = as_stream(stream);
+    dim3 grid(grad_blocks(d), d->N);
+    actor_grad_kernel<<<grid, kGradThreads, 0, s>>>(*d, d->partials);
+    if (int rc = check_launch("actor_grad_kernel")) return rc;
+    return run_reduce(d, 1, 1, !(d->flags & IA2C_FLAG_SKIP_ADAM), s);
+}
+
+extern "C" int ia2c_apply_adam(const ia2c_episode_desc* d, int32_t which, void* stream) {
+    if (int rc = validate(d, "ia2c_apply_adam")) return rc;
+    if (int rc = check_update_ptrs(d, "ia2c_apply_adam")) return rc;
+    IA2C_REQUIRE(which == 0 || which == 1, "ia2c_apply_adam: which=%d", which);
+    return run_reduce(d, which, 0, 1, as_stream(stream));
+}
+
+extern "C" int ia2c_train_episode(const ia2c_episode_desc* d, void* stream) {
+    if (int rc = ia2c_rollout(d, stream)) return rc;
+    if (int rc = ia2c_critic_phase(d, stream)) return rc;
+    return ia2c_actor_phase(d, stream);
+}
+
+extern "C" int ia2c_train_episode_host(const ia2c_episode_desc* d, const float* host_u_action,
+                                       const double* host_u_belief, float* host_loss_out, double* host_ep_return,
+                                       void* stream) {
+    if (int rc = validate(d, "ia2c_train_episode_host")) return rc;
+    IA2C_REQUIRE(!(d->flags & IA2C_FLAG_SKIP_ADAM), "ia2c_train_episode_host: single-rank entry point (SKIP_ADAM set)");
+    cudaStream_t s = as_stream(stream);
+    const size_t n_act = (size_t)(d->T + 1) * d->E * d->N;
+    if (host_u_action) {
+        IA2C_REQUIRE(d->inj_u_action, "ia2c_train_episode_host: desc.inj_u_action staging buffer missing");
+        if (cudaMemcpyAsync(const_cast<float*>(d->inj_u_action), host_u_action, n_act * sizeof(float), cudaMemcpyHostToDevice, s) != cudaSuccess)
+            return check_launch("memcpy H2D u_action");
+    }
+    if (host_u_belief) {
+        IA2C_REQUIRE(d->inj_u_belief, "ia2c_train_episode_host: desc.inj_u_belief staging buffer missing");
+        if (cudaMemcpyAsync(const_cast<double*>(d->inj_u_belief), host_u_belief, n_act * (d->N - 1) * sizeof(double), cudaMemcpyHostToDevice, s) != cudaSuccess)
+            return check_launch("memcpy H2D u_belief");
+    }
+    if (int rc = ia2c_train_episode(d, stream)) return rc;
+    if (host_loss_out && cudaMemcpyAsync(host_loss_out, d->loss_out, 2 * (size_t)d->N * sizeof(float), cudaMemcpyDeviceToHost, s) != cudaSuccess)
+        return check_launch("memcpy D2H loss");
+    if (host_ep_return && cudaMemcpyAsync(host_ep_return, d->ep_return, (size_t)d->E * sizeof(double), cudaMemcpyDeviceToHost, s) != cudaSuccess)
+        return check_launch("memcpy D2H ep_return");
+    if (cudaStreamSynchronize(s) != cudaSuccess) return check_launch("stream sync");
+    return 0;
+}

@@ -1,0 +1,341 @@
+"""Actor / critic networks on the GPU behind the reference's ``ac_nets`` class API.
+
+Reference interface mirrored here (thinclab/IA2C, ac_nets.py):
+  * ``hidden_size = 6``                                                         :24
+  * ``NeuralNet(state_dim, action_dim, b_actor=False)`` with ``l1, l2, l3``      :26-41
+  * ``CriticNetwork(name, n_features, critic_actions, lr, cuda=False)``:
+    ``net, loss, optimizer, num_outs, cuda, losses, critic_loss``;
+    ``run_main(obs, grad=False)``, ``batch_update(obs, act, target, action_distribution=False)``  :43-80
+  * ``ActorNetwork(name, n_features, actor_actions, lr, beta, cuda=False)``:
+    ``net, optimizer, num_outs, cuda, beta, losses, actor_loss``;
+    ``sample_action(obs, grad=False)``, ``action_distribution(obs, grad=False)``,
+    ``batch_update(obs, act, adv, retain=False)`` (never zeroes its gradients, Q2)            :83-127
+
+Every forward, backward, loss, sampler and optimiser step is a kernel of libia2c_b200.so.  torch is
+used for device memory, and its autograd ENGINE only as plumbing between our custom Functions and the
+ad-hoc graphs the reference's scripts build around them (targets / advantages that carry gradient:
+SURVEY.md Q7, Q8).  Inputs may live on the CPU (the scripts create CPU tensors); outputs are returned
+on the input's device.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+hidden_size = 6
+
+
+def n_params(state_dim, action_dim):
+    return hidden_size * state_dim + hidden_size + hidden_size * hidden_size + hidden_size + action_dim * hidden_size + action_dim
+
+
+def _device():
+    _lib.require_cuda()
+    return torch.device(f"cuda:{torch.cuda.current_device()}")
+
+
+class _MLPFunction(torch.autograd.Function):
+    """y = NeuralNet(x) on device tensors; backward = ia2c_mlp_backward (closed form, no torch ops)."""
+
+    @staticmethod
+    def forward(ctx, x, flat, state_dim, action_dim, softmax):
+        lib = _lib.load()
+        x2 = x.detach().reshape(-1, state_dim).to(torch.float32).contiguous()
+        rows = x2.shape[0]
+        y = torch.empty(rows, action_dim, dtype=torch.float32, device=x2.device)
+        _lib.check(lib.ia2c_mlp_forward(_lib.ptr(flat.detach()), _lib.ptr(x2), _lib.ptr(y), rows, state_dim,
+                                        action_dim, 1, int(softmax), _lib.stream_ptr()), "ia2c_mlp_forward")
+        ctx.save_for_backward(x2, flat)
+        ctx.dims = (state_dim, action_dim, softmax, tuple(x.shape))
+        return y.reshape(*x.shape[:-1], action_dim)
+
+    @staticmethod
+    def backward(ctx, gy):
+        lib = _lib.load()
+        x2, flat = ctx.saved_tensors
+        state_dim, action_dim, softmax, xshape = ctx.dims
+        rows = x2.shape[0]
+        dy = gy.reshape(rows, action_dim).to(torch.float32).contiguous()
+        grad = torch.empty_like(flat)
+        dx = torch.empty_like(x2) if ctx.needs_input_grad[0] else None
+        ws = torch.empty(lib.ia2c_mlp_backward_workspace(rows, state_dim, action_dim), dtype=torch.float32,
+                         device=x2.device)
+        _lib.check(lib.ia2c_mlp_backward(_lib.ptr(flat.detach()), _lib.ptr(x2), _lib.ptr(dy), _lib.ptr(grad),
+                                         _lib.ptr(dx), _lib.ptr(ws), rows, state_dim, action_dim, int(softmax), 0,
+                                         _lib.stream_ptr()), "ia2c_mlp_backward")
+        return (dx.reshape(xshape) if dx is not None else None), grad, None, None, None
+
+
+class _CriticLossFunction(torch.autograd.Function):
+    """mean((target - Q[act])^2): ia2c_critic_loss gives the loss, dQ and dtarget in one kernel."""
+
+    @staticmethod
+    def forward(ctx, Q, act, target):
+        lib = _lib.load()
+        O = Q.shape[-1]
+        q2 = Q.detach().reshape(-1, O).contiguous()
+        B = q2.shape[0]
+        a = act.reshape(-1).to(torch.int32).contiguous()
+        t = target.detach().reshape(-1).to(torch.float32).contiguous()
+        if a.numel() != B or t.numel() != B:
+            raise ValueError(f"critic loss: {B} rows of Q but {a.numel()} actions / {t.numel()} targets")
+        loss = torch.empty((), dtype=torch.float32, device=q2.device)
+        dQ = torch.empty_like(q2)
+        dT = torch.empty_like(t)
+        ws = torch.empty(lib.ia2c_loss_workspace(B), dtype=torch.float32, device=q2.device)
+        _lib.check(lib.ia2c_critic_loss(_lib.ptr(q2), _lib.ptr(a), _lib.ptr(t), _lib.ptr(loss), _lib.ptr(dQ),
+                                        _lib.ptr(dT), _lib.ptr(ws), B, O, _lib.stream_ptr()), "ia2c_critic_loss")
+        ctx.save_for_backward(dQ, dT)
+        ctx.shapes = (tuple(Q.shape), tuple(target.shape))
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        dQ, dT = ctx.saved_tensors
+        qs, ts = ctx.shapes
+        return (dQ * g).reshape(qs), None, (dT * g).reshape(ts) if ctx.needs_input_grad[2] else None
+
+
+class _ActorLossFunction(torch.autograd.Function):
+    """mean(adv * (-log q[a]) - beta * H(q)) with Categorical(probs=p) semantics: ia2c_actor_loss."""
+
+    @staticmethod
+    def forward(ctx, probs, act, adv, beta):
+        lib = _lib.load()
+        O = probs.shape[-1]
+        p2 = probs.detach().reshape(-1, O).contiguous()
+        B = p2.shape[0]
+        a = act.reshape(-1).to(torch.int32).contiguous()
+        ad = adv.detach().reshape(-1).to(torch.float32).contiguous()
+        if a.numel() != B or ad.numel() != B:
+            raise ValueError(f"actor loss: {B} rows of probs but {a.numel()} actions / {ad.numel()} advantages")
+        loss = torch.empty((), dtype=torch.float32, device=p2.device)
+        dP = torch.empty_like(p2)
+        dA = torch.empty_like(ad)
+        status = torch.zeros(1, dtype=torch.int32, device=p2.device)
+        ws = torch.empty(lib.ia2c_loss_workspace(B), dtype=torch.float32, device=p2.device)
+        _lib.check(lib.ia2c_actor_loss(_lib.ptr(p2), _lib.ptr(a), _lib.ptr(ad), float(beta), _lib.ptr(loss),
+                                       _lib.ptr(dP), _lib.ptr(dA), _lib.ptr(status), _lib.ptr(ws), B, O,
+                                       _lib.stream_ptr()), "ia2c_actor_loss")
+        ctx.save_for_backward(dP, dA)
+        ctx.shapes = (tuple(probs.shape), tuple(adv.shape))
+        _ActorLossFunction.last_status = status
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        dP, dA = ctx.saved_tensors
+        ps, as_ = ctx.shapes
+        return (dP * g).reshape(ps), None, (dA * g).reshape(as_) if ctx.needs_input_grad[2] else None, None
+
+
+class _LinearView:
+    """``net.l1`` / ``l2`` / ``l3``: weight and bias views into the flat parameter vector."""
+
+    def __init__(self, flat, w_off, out_f, in_f):
+        self.in_features, self.out_features = in_f, out_f
+        self._flat, self._w, self._b = flat, w_off, w_off + out_f * in_f
+
+    @property
+    def weight(self):
+        return self._flat.data[self._w:self._b].view(self.out_features, self.in_features)
+
+    @property
+    def bias(self):
+        return self._flat.data[self._b:self._b + self.out_features]
+
+
+class NeuralNet(nn.Module):
+    """in -> 6 -> 6 -> out MLP (ReLU, optional softmax) whose parameters are ONE flat CUDA vector in
+    nn.Linear state_dict order.  Initial values are drawn exactly as the reference draws them
+    (three nn.Linear default inits from torch's CPU generator, in l1, l2, l3 order)."""
+
+    def __init__(self, state_dim, action_dim, b_actor=False):
+        super().__init__()
+        dev = _device()
+        self.state_dim, self.action_dim, self.b_actor = int(state_dim), int(action_dim), bool(b_actor)
+        l1 = nn.Linear(state_dim, hidden_size)
+        l2 = nn.Linear(hidden_size, hidden_size)
+        l3 = nn.Linear(hidden_size, action_dim)
+        flat = torch.cat([t.detach().reshape(-1) for l in (l1, l2, l3) for t in (l.weight, l.bias)])
+        self.flat = nn.Parameter(flat.to(dev))
+        o1 = 0
+        o2 = o1 + hidden_size * state_dim + hidden_size
+        o3 = o2 + hidden_size * hidden_size + hidden_size
+        self.l1 = _LinearView(self.flat, o1, hidden_size, state_dim)
+        self.l2 = _LinearView(self.flat, o2, hidden_size, hidden_size)
+        self.l3 = _LinearView(self.flat, o3, action_dim, hidden_size)
+
+    def forward(self, s):
+        dev = self.flat.device
+        x = s if (isinstance(s, torch.Tensor) and s.device == dev) else torch.as_tensor(s).to(dev)
+        y = _MLPFunction.apply(x.float(), self.flat, self.state_dim, self.action_dim, self.b_actor)
+        return y
+
+    # state_dict in the reference's key layout
+    def state_dict(self, *args, **kwargs):
+        return {f"l{i}.{k}": getattr(getattr(self, f"l{i}"), k).detach().clone()
+                for i in (1, 2, 3) for k in ("weight", "bias")}
+
+    def load_state_dict(self, sd, strict=True):
+        with torch.no_grad():
+            for i in (1, 2, 3):
+                for k in ("weight", "bias"):
+                    getattr(getattr(self, f"l{i}"), k).copy_(torch.as_tensor(sd[f"l{i}.{k}"]))
+
+    def load_flat(self, flat):
+        with torch.no_grad():
+            self.flat.copy_(torch.as_tensor(np.asarray(flat), dtype=torch.float32))
+
+
+class Adam(torch.optim.Optimizer):
+    """torch.optim.Adam-compatible front (defaults betas .9/.999, eps 1e-8) whose ``step`` is the
+    ``ia2c_adam_step`` kernel over flat parameter vectors.  The step counter lives on the device."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        lib = _lib.load()
+        for group in self.param_groups:
+            for p in group["params"]:
+                if p.grad is None:
+                    continue
+                if not p.is_cuda:
+                    raise _lib.IA2CError("ia2c_b200.Adam only steps CUDA parameters")
+                st = self.state[p]
+                if not st:
+                    st["exp_avg"] = torch.zeros_like(p).reshape(-1)
+                    st["exp_avg_sq"] = torch.zeros_like(p).reshape(-1)
+                    st["step"] = torch.zeros(1, dtype=torch.int32, device=p.device)
+                g = p.grad.reshape(-1).contiguous()
+                _lib.check(lib.ia2c_adam_step(_lib.ptr(p.data.view(-1)), _lib.ptr(g), None, _lib.ptr(st["exp_avg"]),
+                                              _lib.ptr(st["exp_avg_sq"]), _lib.ptr(st["step"]), group["lr"],
+                                              group["betas"][0], group["betas"][1], group["eps"], 1, p.numel(),
+                                              _lib.stream_ptr()), "ia2c_adam_step")
+
+
+def _index_like(act, lead_shape, who):
+    """The reference does ``act.squeeze(-1)``; with one env and a [T,E] action tensor that also squeezes the
+    ENV axis and silently trains on a broadcast [T,T] loss.  We reject that case."""
+    idx = act.squeeze(-1)
+    if tuple(idx.shape) != tuple(lead_shape):
+        raise ValueError(f"{who}: action tensor of shape {tuple(act.shape)} does not index outputs of shape "
+                         f"{tuple(lead_shape)} after squeeze(-1) (with n_envs == 1 the reference's squeeze drops the "
+                         f"env axis and trains on a broadcast [T,T] loss; this implementation refuses that input)")
+    return idx
+
+
+class CriticNetwork:
+    def __init__(self, name, n_features, critic_actions, lr, cuda=False):
+        self.name = name
+        self.num_outs = critic_actions
+        self.net = NeuralNet(n_features, critic_actions)
+        self.loss = nn.MSELoss()
+        self.optimizer = Adam(self.net.parameters(), lr=lr)
+        self.cuda = cuda
+        self.losses = []
+
+    def run_main(self, obs, grad=False):
+        in_dev = obs.device if isinstance(obs, torch.Tensor) else torch.device("cpu")
+        if not grad:
+            with torch.no_grad():
+                out = self.net(obs)
+        else:
+            out = self.net(obs)
+        return out.to(in_dev)
+
+    def batch_update(self, obs, act, target, action_distribution=False):
+        dev = self.net.flat.device
+        self.optimizer.zero_grad()
+        Q = self.net.forward(obs)
+        target_d = target.to(dev)  # differentiable copy: gradient flows back into the caller's graph (Q8)
+        if not action_distribution:
+            idx = _index_like(torch.as_tensor(act), Q.shape[:-1], "CriticNetwork.batch_update").to(dev)
+            loss = _CriticLossFunction.apply(Q, idx, target_d)
+        else:
+            dot_prd = (Q * torch.as_tensor(act).to(dev)).sum(-1, keepdims=True)
+            loss = _CriticLossFunction.apply(dot_prd, torch.zeros(dot_prd.shape[:-1], dtype=torch.int32, device=dev),
+                                             target_d)
+        loss.backward()
+        self.optimizer.step()
+        get_loss = loss.detach().cpu().numpy()
+        self.losses.append(get_loss)
+        if len(self.losses) > 20:
+            del self.losses[0]
+        self.critic_loss = np.mean(self.losses)
+
+
+class ActorNetwork:
+    _instances = 0
+
+    def __init__(self, name, n_features, actor_actions, lr, beta, cuda=False):
+        self.name = name
+        self.num_outs = actor_actions
+        self.net = NeuralNet(n_features, actor_actions, b_actor=True)
+        self.optimizer = Adam(self.net.parameters(), lr=lr)
+        self.cuda = cuda
+        self.beta = beta
+        self.losses = []
+        # device sampler stream: keyed from torch's seed WITHOUT drawing from the generator (a draw here
+        # would shift the initial weights of every network constructed afterwards vs the reference)
+        ActorNetwork._instances += 1
+        self._seed = (torch.initial_seed() * 0x9E3779B97F4A7C15 + ActorNetwork._instances) & (2 ** 64 - 1)
+        self._calls = 0
+        self._replay = None
+        self.last_probs = None
+
+    def replay(self, actions):
+        """Inject recorded action samples (an iterable of per-call tensors/arrays): subsequent
+        ``sample_action`` calls return them instead of the device sampler's draw (parity under replay)."""
+        self._replay = iter(actions) if actions is not None else None
+
+    def sample_action(self, obs, grad=False):
+        lib = _lib.load()
+        dev = self.net.flat.device
+        in_dev = obs.device if isinstance(obs, torch.Tensor) else torch.device("cpu")
+        x = torch.as_tensor(obs).to(dev, torch.float32)
+        lead = x.shape[:-1]
+        x2 = x.reshape(-1, self.net.state_dim).contiguous()
+        rows = x2.shape[0]
+        actions = torch.empty(rows, dtype=torch.int64, device=dev)
+        probs = torch.empty(rows, self.num_outs, dtype=torch.float32, device=dev)
+        _lib.check(lib.ia2c_actor_sample(_lib.ptr(self.net.flat.detach()), _lib.ptr(x2), None, _lib.ptr(actions),
+                                         _lib.ptr(probs), rows, self.net.state_dim, self.num_outs, self._seed,
+                                         self._calls, _lib.stream_ptr()), "ia2c_actor_sample")
+        self._calls += 1
+        self.last_probs = probs
+        if self._replay is not None:
+            return torch.as_tensor(np.asarray(next(self._replay))).reshape(lead).to(in_dev, torch.int64)
+        return actions.reshape(lead).to(in_dev)
+
+    def action_distribution(self, obs, grad=False):
+        in_dev = obs.device if isinstance(obs, torch.Tensor) else torch.device("cpu")
+        if not grad:
+            with torch.no_grad():
+                out = self.net(obs)
+        else:
+            out = self.net(obs)
+        return out.to(in_dev)
+
+    def batch_update(self, obs, act, adv, retain=False):
+        dev = self.net.flat.device
+        probs = self.net.forward(obs)
+        idx = _index_like(torch.as_tensor(act), probs.shape[:-1], "ActorNetwork.batch_update").to(dev)
+        adv_d = adv.to(dev)  # differentiable copy (the advantage may carry gradient, Q7)
+        if adv_d.dim() == probs.dim() and adv_d.shape[-1] == 1:
+            adv_d = adv_d.squeeze(-1)
+        loss = _ActorLossFunction.apply(probs, idx, adv_d, self.beta)
+        loss.backward(retain_graph=retain)      # NO zero_grad: gradients accumulate across updates (Q2)
+        self.optimizer.step()
+        get_loss = loss.detach().cpu().numpy()
+        if int(_ActorLossFunction.last_status.item()):  # the reference's Categorical validation raises here
+            raise ValueError("Expected parameter probs of distribution Categorical to satisfy the constraint Simplex()")
+        self.losses.append(get_loss)
+        if len(self.losses) > 20:
+            del self.losses[0]
+        self.actor_loss = np.mean(self.losses)

@@ -1,0 +1,213 @@
+"""IA2CTrainer — the whole episode of ia2c.py (rollout + critic phase + actor phase) on the GPU.
+
+Reference path covered (thinclab/IA2C): the body of the episode loop, ia2c.py:62-131, with its
+hyper-parameters (ia2c.py:25-31,40,43-46), for E batched Org instances and N agents
+(N=2 is the reference; N>2 is the builder-defined "Org-N" extension).
+
+Everything numeric is a kernel of libia2c_b200.so driven through ``ia2c_episode_desc``; this class
+only owns the device buffers (torch tensors), the optional replay tapes, the multi-GPU all-reduce
+(torch.distributed / NCCL, one per optimiser phase) and the loss windows / return statistics that
+ia2c.py prints (ia2c.py:131-134; ac_nets.py:77-80,124-127).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .nets import hidden_size
+
+N_FEATURES, N_ACTIONS, N_JOINT = 6, 3, 9
+
+
+def reference_init(n_agents, n_models, seed=None):
+    """Initial parameters drawn the way ia2c.py:47-50,61 draws them: critics 1..N then actors 1..N
+    (nn.Linear default init from torch's CPU generator), then one random model matrix per agent from
+    numpy's global generator.  Returns (actor [N,105], critic [N,147], filter_action [N,M,3])."""
+    if seed is not None:
+        torch.manual_seed(seed)
+        np.random.seed(seed)
+
+    def net(out):
+        ls = (nn.Linear(N_FEATURES, hidden_size), nn.Linear(hidden_size, hidden_size), nn.Linear(hidden_size, out))
+        return torch.cat([t.detach().reshape(-1) for l in ls for t in (l.weight, l.bias)]).numpy()
+
+    critic = np.stack([net(N_JOINT) for _ in range(n_agents)])
+    actor = np.stack([net(N_ACTIONS) for _ in range(n_agents)])
+    fa = []
+    for _ in range(n_agents):
+        m = np.random.rand(n_models, N_ACTIONS)
+        m /= np.sum(m, axis=1)[:, np.newaxis]
+        fa.append(m)
+    return actor, critic, np.stack(fa)
+
+
+class IA2CTrainer:
+    def __init__(self, num_envs, n_agents=2, n_models=5, steps_per_episode=30, max_episode_steps=30,
+                 lr_critic=0.0002, lr_actor=0.0001, beta=0.001, gamma=0.9, seed=0, device=None,
+                 rank=0, world_size=1, process_group=None, dumps=False, fused_rollout=False, init=None):
+        _lib.require_cuda()
+        self.lib = _lib.load()
+        self.rank, self.world = int(rank), int(world_size)
+        self.pg = process_group
+        if num_envs % self.world:
+            raise ValueError("num_envs must be divisible by world_size (envs are sharded across ranks)")
+        self.E_total = int(num_envs)
+        self.E = self.E_total // self.world
+        self.N, self.M, self.T = int(n_agents), int(n_models), int(steps_per_episode)
+        self.K = self.N - 1
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.episode = 0
+        self.seed = int(seed)
+        dev, E, N, K, M, T = self.device, self.E, self.N, self.K, self.M, self.T
+
+        def z(shape, dtype):
+            return torch.zeros(shape, dtype=dtype, device=dev)
+
+        f32, f64, u8, i32 = torch.float32, torch.float64, torch.uint8, torch.int32
+        self.actor_params, self.critic_params = z((N, _lib.ACTOR_P), f32), z((N, _lib.CRITIC_P), f32)
+        self.actor_grad, self.critic_grad = z((N, _lib.ACTOR_P + 1), f32), z((N, _lib.CRITIC_P + 1), f32)
+        self.actor_grad_accum = z((N, _lib.ACTOR_P), f32)
+        self.actor_m, self.actor_v = z((N, _lib.ACTOR_P), f32), z((N, _lib.ACTOR_P), f32)
+        self.critic_m, self.critic_v = z((N, _lib.CRITIC_P), f32), z((N, _lib.CRITIC_P), f32)
+        self.actor_step, self.critic_step = z((N,), i32), z((N,), i32)
+        self.loss_out = z((2, N), f32)
+        self.filter_action = z((N, M, N_ACTIONS), f64)
+        self.env_state, self.env_hist = z((E,), i32), z((E,), f64)
+        self.env_cls, self.env_elapsed = z((E, 2), u8), z((E,), i32)
+        self.ep_return = z((E,), f64)
+        self.obs, self.reward = z((T + 1, E, N_FEATURES), f32), z((T, E), f32)
+        self.act, self.partner_true, self.partner_pred = z((T + 1, E, N), u8), z((T + 1, E, N), u8), z((T + 1, E, N), u8)
+        self.belief_records = z((E, N, K, _lib.BELIEF_RECORD), u8)
+        self.inj_actions = self.inj_u_action = self.inj_u_belief = None
+        self.dumps = bool(dumps)
+        if dumps:
+            self.state_trace, self.reward_f64 = z((T, E), i32), z((T, E), f64)
+            self.pred_dump, self.belief_dump = z((T + 1, E, N, K), u8), z((T + 1, E, N, K, M), u8)
+            self.adv_dump, self.target_dump = z((N, T, E), f32), z((N, T, E), f32)
+        self.desc = _lib.EpisodeDesc()
+        d = self.desc
+        d.E, d.E_total, d.env_offset = E, self.E_total, self.rank * E
+        d.N, d.T, d.M, d.max_episode_steps = N, T, M, int(max_episode_steps or 0)
+        d.gamma, d.beta, d.lr_actor, d.lr_critic = gamma, beta, lr_actor, lr_critic
+        d.seed, d.episode = self.seed, 0
+        d.flags = (_lib.FLAG_FUSED_ROLLOUT if fused_rollout else 0) | (_lib.FLAG_SKIP_ADAM if self.world > 1 else 0)
+        for name in ("actor_params", "actor_grad", "actor_grad_accum", "actor_m", "actor_v", "critic_params",
+                     "critic_grad", "critic_m", "critic_v", "actor_step", "critic_step", "loss_out", "filter_action",
+                     "env_state", "env_hist", "env_cls", "env_elapsed", "ep_return", "obs", "reward", "act",
+                     "partner_true", "partner_pred", "belief_records"):
+            setattr(d, name, getattr(self, name).data_ptr())
+        if dumps:
+            for name in ("state_trace", "reward_f64", "pred_dump", "belief_dump", "adv_dump", "target_dump"):
+                setattr(d, name, getattr(self, name).data_ptr())
+        n_part = int(self.lib.ia2c_episode_partials_floats(C.byref(d)))
+        self.partials = z((n_part,), f32)
+        d.partials, d.partials_floats = self.partials.data_ptr(), n_part
+        # host-side bookkeeping the reference prints (ia2c.py:131-134)
+        self.critic_losses, self.actor_losses, self.reward_lst = [], [], []
+        self._h_loss = torch.zeros(2, N, dtype=f32).pin_memory()
+        self._h_return = torch.zeros(E, dtype=f64).pin_memory()
+        if init is None:
+            init = reference_init(N, M)
+        self.load_init(*init)
+
+    # ------------------------------------------------------------------ parameters
+    def load_init(self, actor, critic, filter_action):
+        self.actor_params.copy_(torch.as_tensor(np.asarray(actor), dtype=torch.float32))
+        self.critic_params.copy_(torch.as_tensor(np.asarray(critic), dtype=torch.float32))
+        self.filter_action.copy_(torch.as_tensor(np.asarray(filter_action), dtype=torch.float64))
+
+    # ------------------------------------------------------------------ injected randomness
+    def inject(self, actions=None, u_action=None, u_belief=None):
+        """Replay tapes for the NEXT episodes (kept until changed): ``actions`` uint8[T+1,E,N] (the
+        reference's sampled actions), ``u_action`` float32[T+1,E,N] (uniforms for the inverse-CDF sampler),
+        ``u_belief`` float64[T+1,E,N,K] (the belief filter's ``np.random.rand`` draws).  None -> Philox."""
+        T, E, N, K, dev = self.T, self.E, self.N, self.K, self.device
+
+        def put(x, dtype, shape):
+            if x is None:
+                return None
+            t = torch.as_tensor(np.asarray(x) if not isinstance(x, torch.Tensor) else x).to(dev, dtype).contiguous()
+            assert tuple(t.shape) == shape, (tuple(t.shape), shape)
+            return t
+
+        self.inj_actions = put(actions, torch.uint8, (T + 1, E, N))
+        self.inj_u_action = put(u_action, torch.float32, (T + 1, E, N))
+        self.inj_u_belief = put(u_belief, torch.float64, (T + 1, E, N, K))
+        self.desc.inj_actions = self.inj_actions.data_ptr() if self.inj_actions is not None else None
+        self.desc.inj_u_action = self.inj_u_action.data_ptr() if self.inj_u_action is not None else None
+        self.desc.inj_u_belief = self.inj_u_belief.data_ptr() if self.inj_u_belief is not None else None
+
+    # ------------------------------------------------------------------ one episode
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def rollout(self):
+        self.desc.episode = self.episode
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.ia2c_rollout(C.byref(self.desc), self._stream()), "ia2c_rollout")
+
+    def update(self):
+        d, s = C.byref(self.desc), self._stream()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.ia2c_critic_phase(d, s), "ia2c_critic_phase")
+            if self.world > 1:
+                self._allreduce(self.critic_grad)
+                _lib.check(self.lib.ia2c_apply_adam(d, 0, s), "ia2c_apply_adam(critic)")
+            _lib.check(self.lib.ia2c_actor_phase(d, s), "ia2c_actor_phase")
+            if self.world > 1:
+                self._allreduce(self.actor_grad)
+                _lib.check(self.lib.ia2c_apply_adam(d, 1, s), "ia2c_apply_adam(actor)")
+
+    def _allreduce(self, buf):
+        import torch.distributed as dist
+
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.pg)
+
+    def train_episode(self, sync_stats=False):
+        """One episode: rollout, critic update, actor update.  Asynchronous unless ``sync_stats``."""
+        self.rollout()
+        self.update()
+        self.episode += 1
+        if sync_stats:
+            return self.read_stats()
+
+    def train_episode_host(self, host_u_action, host_u_belief):
+        """End-to-end form with HOST inputs/outputs: pinned uniforms in, losses + episode returns out;
+        the copies and a stream sync are inside the call (single rank)."""
+        if self.world > 1:
+            raise _lib.IA2CError("train_episode_host is the single-rank entry point")
+        if self.inj_u_action is None or self.inj_u_belief is None:
+            T, E, N, K = self.T, self.E, self.N, self.K
+            self.inject(u_action=torch.zeros(T + 1, E, N), u_belief=torch.zeros(T + 1, E, N, K, dtype=torch.float64))
+        self.desc.episode = self.episode
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.ia2c_train_episode_host(
+                C.byref(self.desc), host_u_action.data_ptr(), host_u_belief.data_ptr(), self._h_loss.data_ptr(),
+                self._h_return.data_ptr(), self._stream()), "ia2c_train_episode_host")
+        self.episode += 1
+        return self._record_stats()
+
+    def read_stats(self):
+        self._h_loss.copy_(self.loss_out, non_blocking=True)
+        self._h_return.copy_(self.ep_return, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return self._record_stats()
+
+    def _record_stats(self):
+        loss = self._h_loss.numpy().copy()
+        ret = self._h_return.numpy().copy()
+        self.critic_losses.append(loss[0]), self.actor_losses.append(loss[1])
+        del self.critic_losses[:-20], self.actor_losses[:-20]      # 20-deep loss windows (ac_nets.py:77-80)
+        self.reward_lst.append(ret)
+        del self.reward_lst[:-50]                                  # mean of the last 50 (ia2c.py:134)
+        return dict(critic_loss=loss[0], actor_loss=loss[1], ep_return=ret,
+                    critic_loss_window=np.mean(self.critic_losses, axis=0),
+                    actor_loss_window=np.mean(self.actor_losses, axis=0), mean_return=np.mean(self.reward_lst))
+
+    # ------------------------------------------------------------------ accounting
+    def agent_steps_per_episode(self):
+        return self.E_total * self.N * self.T

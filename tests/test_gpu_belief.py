@@ -1,0 +1,116 @@
+"""GPU parity: belief-filter kernels vs golden vectors of the real class and vs the oracle.  Bit-exact."""
+import numpy as np
+import pytest
+
+from oracle import belief as B
+from oracle import philox as P
+from oracle.loops import mode3, others_of
+from tests.helpers import dev, host
+
+pytestmark = pytest.mark.gpu
+
+
+def _dense(fa, lik, prev, u):
+    import torch
+    from ia2c_b200 import _lib
+    lib = _lib.load()
+    R, A = lik.shape
+    M = prev.shape[1]
+    ap = torch.empty(R, dtype=torch.int64, device="cuda")
+    bp = torch.empty(R, M, dtype=torch.float64, device="cuda")
+    pred = torch.empty(R, A, dtype=torch.float64, device="cuda")
+    _lib.check(lib.ia2c_belief_update_dense(_lib.ptr(dev(fa)), _lib.ptr(dev(lik)), _lib.ptr(dev(prev)), _lib.ptr(dev(u.reshape(-1))),
+                                            _lib.ptr(ap), _lib.ptr(bp), _lib.ptr(pred), R, M, A, _lib.stream_ptr()))
+    return host(ap), host(bp), host(pred)
+
+
+@pytest.mark.parametrize("tag", ["rand5", "rand3", "rand5x5", "org_known", "hvt_known"])
+def test_dense_vs_golden_and_oracle(golden, tag):
+    g = golden("belief_vectors.npz")
+    fa = g[f"{tag}/filterAction"]
+    for t in range(0, g[f"{tag}/obs"].shape[0], 3):
+        lik, prev, u = g[f"{tag}/obs"][t], g[f"{tag}/prev"][t], g[f"{tag}/u"][t]
+        ap, bp, pred = _dense(fa, lik, prev, u)
+        assert np.array_equal(bp, g[f"{tag}/bprime"][t])                    # vs the real class: bit-exact
+        assert np.array_equal(ap, g[f"{tag}/ap"][t])
+        np.testing.assert_allclose(pred, g[f"{tag}/prediction"][t], rtol=2e-15, atol=0)
+        oap, obp, opred = B.belief_update(fa, lik, prev, u)
+        assert np.array_equal(pred, opred) and np.array_equal(ap, oap)      # vs the oracle: bit-exact incl. prediction
+
+
+def test_dense_generic_dims_and_ragged_rows():
+    rng = np.random.RandomState(0)
+    for M, A, R in ((2, 2, 1), (4, 3, 257), (7, 8, 1000), (8, 2, 33)):
+        fa = rng.rand(M, A)
+        fa /= fa.sum(1, keepdims=True)
+        prev = np.rint(rng.dirichlet(np.ones(M), R) * 100) / 100
+        lik = rng.rand(R, A)
+        u = rng.rand(R)
+        ap, bp, pred = _dense(fa, lik, prev, u)
+        oap, obp, opred = B.belief_update(fa, lik, prev, u)
+        assert np.array_equal(bp, obp) and np.array_equal(ap, oap) and np.array_equal(pred, opred)
+
+
+def test_class_api_consumes_numpy_stream_like_reference(golden):
+    from ia2c_b200.belief import BeliefFilter
+    g = golden("belief_vectors.npz")
+    np.random.seed(11)
+    bf = BeliefFilter(5, 3, 256)
+    assert np.array_equal(bf.filterAction, g["rand5/filterAction"]) and np.array_equal(bf.prior, g["rand5/prior0"])
+    assert np.array_equal(bf.filters, bf.filterAction.T)
+    real_rand = np.random.rand
+    for t in range(10):
+        tape = g["rand5/u"][t]
+        np.random.rand = lambda *shape: tape.copy()
+        try:
+            ap, bprime, pred = bf.update(g["rand5/obs"][t], g["rand5/prev"][t])
+        finally:
+            np.random.rand = real_rand
+        assert ap.dtype == np.int64 and np.array_equal(ap, g["rand5/ap"][t]) and np.array_equal(bprime, g["rand5/bprime"][t])
+    known = BeliefFilter(3, 3, 64, known="org")
+    assert np.array_equal(known.filterAction, g["org_known/filterAction"])
+
+
+def _pairs_oracle(fa, act, prior, u):
+    """act [E,N]; prior [E,N,K,M]; u [E,N,K] -> ap [E,N,K], bprime [E,N,K,M] via the oracle."""
+    E, N = act.shape
+    K = N - 1
+    ap = np.zeros((E, N, K), dtype=np.int64)
+    bp = np.zeros_like(prior)
+    for i in range(N):
+        for jj, j in enumerate(others_of(i, N)):
+            a, b, _ = B.belief_update(fa[i], B.likelihood_from_action(act[:, j], 3), prior[:, i, jj], u[:, i, jj])
+            ap[:, i, jj], bp[:, i, jj] = a, b
+    return ap, bp
+
+
+@pytest.mark.parametrize("E,N,M", [(1, 2, 5), (37, 2, 5), (300, 3, 5), (9, 5, 3), (5, 64, 5), (2, 256, 5), (3, 7, 6), (4, 6, 2)])
+def test_pairs_kernel_vs_oracle(E, N, M):
+    import torch
+    from ia2c_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.RandomState(E + N)
+    K = N - 1
+    fa = rng.rand(N, M, 3)
+    fa /= fa.sum(-1, keepdims=True)
+    rec = torch.zeros(E, N, K, 8, dtype=torch.uint8, device="cuda")
+    prior = np.tile(B.uniform_prior(1, M)[0], (E, N, K, 1))
+    for t in range(6):
+        act = rng.randint(0, 3, size=(E, N)).astype(np.uint8)
+        injected = t % 2 == 0
+        if injected:
+            u = rng.rand(E, N, K)
+        else:
+            u = P.uniform_f64(77, P.STREAM_BELIEF, 5, t, (np.arange(E)[:, None, None] + 1000) * N * K + np.arange(N)[None, :, None] * K + np.arange(K)[None, None, :])
+        pred = torch.empty(E, N, K, dtype=torch.uint8, device="cuda")
+        bel = torch.empty(E, N, K, M, dtype=torch.uint8, device="cuda")
+        partner = torch.empty(E, N, dtype=torch.uint8, device="cuda")
+        _lib.check(lib.ia2c_belief_update_pairs(_lib.ptr(rec), _lib.ptr(dev(fa)), _lib.ptr(dev(act)), _lib.ptr(dev(u)) if injected else None,
+                                                _lib.ptr(pred), _lib.ptr(bel), _lib.ptr(partner), E, N, M, int(t == 0), 77, 5, t, 1000,
+                                                _lib.stream_ptr()))
+        oap, obp = _pairs_oracle(fa, act, prior, u)
+        assert np.array_equal(host(pred), oap)
+        assert np.array_equal(host(bel), B.to_hundredths(obp))
+        assert np.array_equal(host(rec)[..., :M], B.to_hundredths(obp)) and np.array_equal(host(rec)[..., 6], oap)
+        assert np.array_equal(host(partner), mode3(oap))
+        prior = obp

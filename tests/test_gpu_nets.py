@@ -1,0 +1,159 @@
+"""GPU parity: actor/critic MLP kernels, losses and Adam (class API through the C ABI) vs golden tapes of
+the real ac_nets classes and vs the oracle.  Tolerance: 1e-5 relative (north star, fp32)."""
+import numpy as np
+import pytest
+
+from oracle import nets as NN
+from tests.helpers import dev, host, rel_err
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-5
+
+
+@pytest.mark.parametrize("tag", ["org", "org9", "taxi", "dense"])
+def test_class_api_vs_golden_updates(golden, tag):
+    import torch
+    import torch.nn.functional as F
+    from ia2c_b200.nets import ActorNetwork, CriticNetwork
+
+    g = golden("acnets_updates.npz")
+    T, E, Fd, J, A, _ = [int(x) for x in g[f"{tag}/dims"]]
+    lr_c, lr_a, beta, gamma = g[f"{tag}/hyper"]
+    critic = CriticNetwork("c", Fd, J, lr_c)
+    actor = ActorNetwork("a", Fd, A, lr_a, beta)
+    critic.net.load_flat(g[f"{tag}/critic_init"])
+    actor.net.load_flat(g[f"{tag}/actor_init"])
+    assert set(critic.net.state_dict()) == {f"l{i}.{k}" for i in (1, 2, 3) for k in ("weight", "bias")}
+    assert tuple(critic.net.l1.weight.shape) == (6, Fd) and tuple(actor.net.l3.weight.shape) == (A, 6)
+    for it in range(3):
+        k = lambda n: torch.from_numpy(g[f"{tag}/{it}/{n}"])
+        obs, nobs = k("obs"), k("nobs")
+        Q = critic.run_main(obs)
+        Pr = actor.action_distribution(obs)
+        assert Q.device.type == "cpu" and tuple(Q.shape) == (T, E, J)
+        assert rel_err(Q.numpy(), k("Q").numpy()) < RTOL and rel_err(Pr.numpy(), k("P").numpy()) < RTOL
+        # the script-side graph around run_main(grad=True) is plain torch on CPU tensors (ia2c.py:108-111)
+        with_grad = bool(g[f"{tag}/{it}/target_has_grad"])
+        qn = (critic.run_main(nobs, grad=with_grad) * F.one_hot(k("cnext"), J).float()).sum(-1, keepdims=True)
+        target = k("rew").unsqueeze(-1) + gamma * k("mask").unsqueeze(-1) * qn
+        assert target.requires_grad == with_grad
+        assert rel_err(target.detach().numpy(), k("target").numpy()) < RTOL
+        critic.batch_update(obs, k("cact"), target)
+        assert rel_err(critic.losses[-1], k("critic_loss").numpy()) < RTOL
+        assert rel_err(host(critic.net.flat.grad), k("critic_grad").numpy()) < RTOL
+        assert rel_err(host(critic.net.flat), k("critic_params").numpy()) < RTOL
+        actor.batch_update(obs, k("aact"), k("adv"))
+        assert rel_err(actor.losses[-1], k("actor_loss").numpy()) < RTOL
+        assert rel_err(host(actor.net.flat.grad), k("actor_grad_accum").numpy()) < RTOL   # never zeroed (Q2)
+        assert rel_err(host(actor.net.flat), k("actor_params").numpy()) < RTOL
+    assert np.isclose(critic.critic_loss, np.mean(critic.losses)) and len(actor.losses) == 3
+
+
+@pytest.mark.parametrize("rows,F,O,softmax", [(1, 6, 3, 1), (1000, 6, 9, 0), (777, 6, 9, 1), (513, 500, 6, 0), (64, 500, 6, 1),
+                                              (300, 11, 25, 1), (129, 70, 2, 0), (5000, 1, 1, 0)])
+def test_mlp_forward_backward_vs_oracle(rows, F, O, softmax):
+    import torch
+    from ia2c_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.RandomState(rows + F + O)
+    flat = (rng.randn(NN.n_params(F, O)) * 0.4).astype(np.float32)
+    x = rng.randn(rows, F).astype(np.float32)
+    if F == 500:
+        x = np.eye(F, dtype=np.float32)[rng.randint(0, F, rows)]
+    dy = rng.randn(rows, O).astype(np.float32)
+    y = torch.empty(rows, O, device="cuda")
+    _lib.check(lib.ia2c_mlp_forward(_lib.ptr(dev(flat)), _lib.ptr(dev(x)), _lib.ptr(y), rows, F, O, 1, softmax, _lib.stream_ptr()))
+    ref, cache = NN.forward(flat.astype(np.float64), x, F, O, softmax=bool(softmax), keep=True)
+    assert rel_err(host(y), ref) < RTOL
+    grad = torch.full((flat.size,), 7.0, device="cuda")
+    dx = torch.empty(rows, F, device="cuda")
+    ws = torch.empty(lib.ia2c_mlp_backward_workspace(rows, F, O), device="cuda")
+    _lib.check(lib.ia2c_mlp_backward(_lib.ptr(dev(flat)), _lib.ptr(dev(x)), _lib.ptr(dev(dy)), _lib.ptr(grad), _lib.ptr(dx), _lib.ptr(ws),
+                                     rows, F, O, softmax, 0, _lib.stream_ptr()))
+    dyp = dy.astype(np.float64)
+    if softmax:
+        dyp = ref * (dyp - (ref * dyp).sum(-1, keepdims=True))
+    gref = NN.backward(flat.astype(np.float64), cache, dyp, F, O)
+    assert rel_err(host(grad), gref) < RTOL
+    W1 = flat[:6 * F].reshape(6, F).astype(np.float64)
+    dz1 = ((dyp @ NN.unpack(flat.astype(np.float64), F, O)[4]) * (cache[4] > 0)) @ NN.unpack(flat.astype(np.float64), F, O)[2] * (cache[2] > 0)
+    assert rel_err(host(dx), dz1 @ W1) < RTOL
+    # accumulate mode adds onto the existing gradient
+    _lib.check(lib.ia2c_mlp_backward(_lib.ptr(dev(flat)), _lib.ptr(dev(x)), _lib.ptr(dev(dy)), _lib.ptr(grad), None, _lib.ptr(ws),
+                                     rows, F, O, softmax, 1, _lib.stream_ptr()))
+    assert rel_err(host(grad), 2 * gref) < RTOL
+
+
+def test_multi_net_forward():
+    import torch
+    from ia2c_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.RandomState(1)
+    nets, rows = 5, 333
+    flat = (rng.randn(nets, 105) * 0.5).astype(np.float32)
+    x = rng.randn(rows, 6).astype(np.float32)
+    y = torch.empty(nets, rows, 3, device="cuda")
+    _lib.check(lib.ia2c_mlp_forward(_lib.ptr(dev(flat)), _lib.ptr(dev(x)), _lib.ptr(y), rows, 6, 3, nets, 1, _lib.stream_ptr()))
+    for n in range(nets):
+        assert rel_err(host(y)[n], NN.forward(flat[n].astype(np.float64), x, 6, 3, softmax=True)) < RTOL
+
+
+def test_sampler_injected_uniforms_and_philox():
+    import torch
+    from ia2c_b200 import _lib
+    from oracle import philox as P
+    lib = _lib.load()
+    rng = np.random.RandomState(2)
+    rows, F, O = 20000, 6, 9
+    flat = (rng.randn(NN.n_params(F, O)) * 0.7).astype(np.float32)
+    x = rng.randn(rows, F).astype(np.float32)
+    u = rng.rand(rows).astype(np.float32)
+    act = torch.empty(rows, dtype=torch.int64, device="cuda")
+    probs = torch.empty(rows, O, device="cuda")
+    _lib.check(lib.ia2c_actor_sample(_lib.ptr(dev(flat)), _lib.ptr(dev(x)), _lib.ptr(dev(u)), _lib.ptr(act), _lib.ptr(probs), rows, F, O, 0, 0, _lib.stream_ptr()))
+    p_ref = NN.forward(flat, x, F, O, softmax=True)
+    assert rel_err(host(probs), p_ref) < RTOL
+    assert np.array_equal(host(act), NN.sample_inverse_cdf(host(probs).astype(np.float64), u))  # exact given the kernel's own probs
+    assert (host(act) != NN.sample_inverse_cdf(p_ref, u)).mean() < 1e-3                          # oracle probs differ by ulps only
+    # Philox path: the uniforms are reproducible by the oracle generator
+    seed, counter = 1234567, (3 << 16) | 17
+    _lib.check(lib.ia2c_actor_sample(_lib.ptr(dev(flat)), _lib.ptr(dev(x)), None, _lib.ptr(act), _lib.ptr(probs), rows, F, O, seed, counter, _lib.stream_ptr()))
+    u2 = P.uniform_f32(seed, P.STREAM_ACTION, 3, 17, np.arange(rows))
+    assert np.array_equal(host(act), NN.sample_inverse_cdf(host(probs).astype(np.float64), u2))
+    freq = np.bincount(host(act), minlength=O) / rows
+    assert np.abs(freq - host(probs).mean(0)).max() < 0.02
+
+
+def test_q15_single_env_squeeze_is_rejected():
+    import torch
+    from ia2c_b200.nets import CriticNetwork
+    c = CriticNetwork("c", 6, 9, 1e-3)
+    obs = torch.zeros(30, 1, 6)
+    with pytest.raises(ValueError, match="squeeze"):
+        c.batch_update(obs, torch.zeros(30, 1), torch.zeros(30, 1, 1))
+    c.batch_update(obs, torch.zeros(30, 1, 1), torch.zeros(30, 1, 1))  # explicit trailing axis is fine
+
+
+def test_adam_matches_oracle_over_many_steps():
+    import torch
+    from ia2c_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.RandomState(5)
+    nets, Pn = 3, 147
+    p0 = rng.randn(nets, Pn).astype(np.float32)
+    p = dev(p0.copy())
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    acc = torch.zeros_like(p)
+    step = torch.zeros(nets, dtype=torch.int32, device="cuda")
+    refs = [NN.AdamRef(Pn, 2e-4) for _ in range(nets)]
+    pr = [p0[n].copy() for n in range(nets)]
+    accr = np.zeros_like(p0)
+    for it in range(25):
+        g = (rng.randn(nets, Pn) * 10 ** rng.uniform(-4, 1)).astype(np.float32)
+        _lib.check(lib.ia2c_adam_step(_lib.ptr(p), _lib.ptr(dev(g)), _lib.ptr(acc), _lib.ptr(m), _lib.ptr(v), _lib.ptr(step),
+                                      2e-4, 0.9, 0.999, 1e-8, nets, Pn, _lib.stream_ptr()))
+        accr = accr + g
+        for n in range(nets):
+            pr[n] = refs[n].step(pr[n], accr[n])
+    assert int(step[0]) == 25
+    assert rel_err(host(p), np.stack(pr)) < 1e-6 and rel_err(host(acc), accr) < 1e-6

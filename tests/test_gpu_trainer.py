@@ -1,0 +1,141 @@
+"""GPU parity: the fused IA2C episode (rollout + critic phase + actor phase through the C ABI) replayed against
+unmodified-reference tapes (N=2) and against the oracle (Org-N, Philox mode)."""
+import numpy as np
+import pytest
+
+from oracle import belief as B
+from oracle import loops as L
+from oracle import philox as P
+from tests.helpers import host, rel_err
+from tests.test_oracle_loops import ia2c_state_from_golden, ia2c_tapes
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-5
+
+
+def make_trainer(E, N, M, init, **kw):
+    from ia2c_b200.trainer import IA2CTrainer
+    return IA2CTrainer(E, n_agents=N, n_models=M, init=init, dumps=True, **kw)
+
+
+@pytest.mark.parametrize("name", ["ia2c_E10.npz", "ia2c_E64.npz"])
+def test_replay_reference_tapes(golden, name):
+    g = golden(name)
+    T, E = int(g["meta_T"]), int(g["meta_n_envs"])
+    st = ia2c_state_from_golden(g)
+    lr_c, lr_a, beta, gamma = g["meta_hyper"]
+    tr = make_trainer(E, 2, 5, (st.actor, st.critic, st.filter_action), lr_critic=lr_c, lr_actor=lr_a, beta=beta, gamma=gamma,
+                      steps_per_episode=T)
+    for ep in range(int(g["meta_episodes"])):
+        sl, actions, u = ia2c_tapes(g, ep)
+        tr.inject(actions=actions, u_belief=u)
+        stats = tr.train_episode(sync_stats=True)
+        es = slice(ep * T, (ep + 1) * T)
+        # bit-exact: env states, rewards (fp64 and the float32 trajectory copy), observations, returns
+        assert np.array_equal(host(tr.state_trace), g["env/state_pre_reset"][es])
+        assert np.array_equal(host(tr.reward_f64), g["env/reward"][es])
+        assert np.array_equal(host(tr.reward), g["env/reward"][es].astype(np.float32))
+        assert np.array_equal(host(tr.obs)[1:], g["env/obs"][es]) and np.array_equal(host(tr.obs)[0], g["env/reset_obs"][ep])
+        assert np.array_equal(stats["ep_return"], g["reward_lst"][ep])
+        # bit-exact: beliefs (hundredths are lossless) and predicted actions
+        for i, f in enumerate(("bf0", "bf1")):
+            assert np.array_equal(host(tr.belief_dump)[:, :, i, 0] / 100.0, g[f"{f}/bprime"][sl])
+            assert np.array_equal(host(tr.pred_dump)[:, :, i, 0], g[f"{f}/ap"][sl])
+        # fp32 within 1e-5: targets, advantages, losses, gradients, post-Adam parameters
+        for i, (c, a) in enumerate((("crit1", "act1"), ("crit2", "act2"))):
+            assert rel_err(host(tr.target_dump)[i], g[f"{c}/upd_target"][ep][..., 0]) < RTOL
+            assert rel_err(stats["critic_loss"][i], g[f"{c}/upd_loss"][ep]) < RTOL
+            assert rel_err(host(tr.critic_grad)[i, :147], g[f"{c}/upd_grad"][ep]) < RTOL
+            assert rel_err(host(tr.critic_params)[i], g[f"{c}/upd_params"][ep]) < RTOL
+            assert rel_err(host(tr.adv_dump)[i], g[f"{a}/upd_adv"][ep][..., 0]) < RTOL
+            assert rel_err(stats["actor_loss"][i], g[f"{a}/upd_loss"][ep]) < RTOL
+            assert rel_err(host(tr.actor_grad_accum)[i], g[f"{a}/upd_grad"][ep]) < RTOL   # running sum (Q2)
+            assert rel_err(host(tr.actor_params)[i], g[f"{a}/upd_params"][ep]) < RTOL
+    assert rel_err(stats["critic_loss_window"], g["critic_loss_window"]) < RTOL
+    assert rel_err(stats["actor_loss_window"], g["actor_loss_window"]) < RTOL
+
+
+def _random_init(N, M, seed):
+    from ia2c_b200.trainer import reference_init
+    return reference_init(N, M, seed=seed)
+
+
+def _compare_with_oracle(tr, st, traj, upd, N):
+    T = st.T
+    assert np.array_equal(host(tr.state_trace), traj["state"])
+    assert np.array_equal(host(tr.reward_f64), traj["reward"])
+    assert np.array_equal(host(tr.obs), traj["obs"])
+    assert np.array_equal(host(tr.act), traj["act"])
+    assert np.array_equal(host(tr.pred_dump), traj["pred"])
+    assert np.array_equal(host(tr.belief_dump), B.to_hundredths(traj["belief"]))
+    true_p, pred_p = L.partner_actions(traj, N)
+    assert np.array_equal(host(tr.partner_true), true_p) and np.array_equal(host(tr.partner_pred), pred_p)
+    assert np.array_equal(host(tr.ep_return), traj["ep_return"])
+    for i in range(N):
+        assert rel_err(host(tr.target_dump)[i], upd["critic_target"][i]) < RTOL
+        assert rel_err(host(tr.critic_grad)[i, :147], upd["critic_grad"][i]) < RTOL
+        assert rel_err(host(tr.critic_grad)[i, 147], upd["critic_loss"][i]) < RTOL
+        assert rel_err(host(tr.critic_params)[i], st.critic[i]) < RTOL
+        assert rel_err(host(tr.adv_dump)[i], upd["adv"][i]) < RTOL
+        assert rel_err(host(tr.actor_grad_accum)[i], upd["actor_grad"][i]) < RTOL
+        assert rel_err(host(tr.actor_grad)[i, 105], upd["actor_loss"][i]) < RTOL
+        assert rel_err(host(tr.actor_params)[i], st.actor[i]) < RTOL
+
+
+@pytest.mark.parametrize("E,N,M,T", [(7, 2, 5, 30), (33, 3, 5, 12), (5, 5, 3, 9), (3, 33, 5, 6), (2, 64, 5, 4)])
+def test_org_n_injected_vs_oracle(E, N, M, T):
+    actor, critic, fa = _random_init(N, M, seed=E + N)
+    st = L.IA2CState(actor=actor.astype(np.float64), critic=critic.astype(np.float64), filter_action=fa, T=T, max_episode_steps=T)
+    tr = make_trainer(E, N, M, (actor, critic, fa), steps_per_episode=T, max_episode_steps=T)
+    rng = np.random.RandomState(N)
+    for ep in range(2):
+        actions = rng.randint(0, 3, size=(T + 1, E, N))
+        if ep == 1:
+            actions[3:6] = actions[3:6, :, :1]  # unanimous stretches hit the 6 / 5 rewards and state 0 / 4
+        u = rng.rand(T + 1, E, N, N - 1)
+        tr.inject(actions=actions, u_belief=u)
+        tr.train_episode(sync_stats=True)
+        traj, upd = L.ia2c_episode(st, E, actions=actions, u_belief=u)
+        _compare_with_oracle(tr, st, traj, upd, N)
+
+
+def test_philox_mode_is_replayable_by_the_oracle():
+    """Performance mode (device Philox sampler): regenerate the uniforms in the oracle, feed the kernel's own
+    sampled actions back as a tape, and require everything else to match; the sampler itself is checked
+    against the oracle's inverse-CDF on the oracle's probabilities (ulp-level flips only)."""
+    E, N, M, T, seed = 64, 2, 5, 30, 99
+    actor, critic, fa = _random_init(N, M, seed=4)
+    st = L.IA2CState(actor=actor.astype(np.float64), critic=critic.astype(np.float64), filter_action=fa, T=T)
+    tr = make_trainer(E, N, M, (actor, critic, fa), seed=seed)
+    for ep in range(2):
+        tr.train_episode(sync_stats=True)
+        idx_a = np.arange(E)[:, None] * N + np.arange(N)[None, :]
+        idx_b = (np.arange(E)[:, None, None] * N + np.arange(N)[None, :, None]) * (N - 1) + np.arange(N - 1)[None, None, :]
+        u_act = np.stack([P.uniform_f32(seed, P.STREAM_ACTION, ep, t, idx_a) for t in range(T + 1)])
+        u_bel = np.stack([P.uniform_f64(seed, P.STREAM_BELIEF, ep, t, idx_b) for t in range(T + 1)])
+        gpu_actions = host(tr.act).astype(np.int64)
+        probe = L.IA2CState(actor=st.actor.copy(), critic=st.critic.copy(), filter_action=fa, T=T)
+        resampled = L.ia2c_rollout(probe, E, u_act=u_act, u_belief=u_bel)["act"]
+        assert (resampled[0] != gpu_actions[0]).mean() < 2e-3          # t=0 has identical inputs on both sides
+        traj, upd = L.ia2c_episode(st, E, actions=gpu_actions, u_belief=u_bel)
+        _compare_with_oracle(tr, st, traj, upd, N)
+    # run-to-run determinism
+    tr2 = make_trainer(E, N, M, (actor, critic, fa), seed=seed)
+    tr2.train_episode(), tr2.train_episode(sync_stats=True)
+    assert np.array_equal(host(tr.act), host(tr2.act)) and np.array_equal(host(tr.actor_params), host(tr2.actor_params))
+
+
+def test_host_entry_point_matches_device_path():
+    import torch
+    E, N, M, T = 48, 2, 5, 30
+    init = _random_init(N, M, seed=8)
+    rng = np.random.RandomState(0)
+    ua = torch.from_numpy(rng.rand(T + 1, E, N).astype(np.float32)).pin_memory()
+    ub = torch.from_numpy(rng.rand(T + 1, E, N, N - 1)).pin_memory()
+    a = make_trainer(E, N, M, init)
+    b = make_trainer(E, N, M, init)
+    out = a.train_episode_host(ua, ub)
+    b.inject(u_action=ua, u_belief=ub)
+    ref = b.train_episode(sync_stats=True)
+    assert np.array_equal(out["ep_return"], ref["ep_return"]) and np.array_equal(out["critic_loss"], ref["critic_loss"])
+    assert np.array_equal(host(a.actor_params), host(b.actor_params))
