@@ -23,6 +23,9 @@
 #include "common.cuh"
 
 namespace ia2c {
+int rollout_fused_supported(int N, int M);                                  // rollout_fused.cu
+int rollout_fused_launch(const ia2c_episode_desc* d, cudaStream_t s);
+
 namespace {
 
 constexpr int F = IA2C_OBS_FEATURES, A = IA2C_AGENT_ACTIONS, J = IA2C_JOINT_ACTIONS;
@@ -358,6 +361,10 @@ extern "C" int ia2c_rollout(const ia2c_episode_desc* d, void* stream) {
     IA2C_REQUIRE(d->env_state && d->env_hist && d->env_cls && d->env_elapsed && d->ep_return && d->belief_records &&
                      d->filter_action, "ia2c_rollout: null env/belief pointer");
     cudaStream_t s = as_stream(stream);
+    if (d->flags & IA2C_FLAG_FUSED_ROLLOUT) {
+        IA2C_REQUIRE(rollout_fused_supported(d->N, d->M), "ia2c_rollout: IA2C_FLAG_FUSED_ROLLOUT needs N<=8 with M=5 (or N=2, M=3); got N=%d M=%d", d->N, d->M);
+        return rollout_fused_launch(d, s);
+    }
     StepArgs S;
     S.d = *d;
     int G = 1;

@@ -18,3 +18,18 @@ def dev(x, dtype=None):
 
 def host(t):
     return t.detach().cpu().numpy()
+
+
+_KEEP = []
+
+
+def dptr(x, dtype=None):
+    """Device pointer of a fresh device copy of x; the tensor is kept alive so the caching allocator cannot
+    hand its memory to the next temporary before the kernel has run."""
+    t = dev(x, dtype)
+    _KEEP.append(t)
+    if len(_KEEP) > 256:
+        import torch
+        torch.cuda.synchronize()
+        del _KEEP[:128]
+    return t.data_ptr()

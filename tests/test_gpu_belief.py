@@ -5,7 +5,7 @@ import pytest
 from oracle import belief as B
 from oracle import philox as P
 from oracle.loops import mode3, others_of
-from tests.helpers import dev, host
+from tests.helpers import dev, dptr, host
 
 pytestmark = pytest.mark.gpu
 
@@ -19,7 +19,7 @@ def _dense(fa, lik, prev, u):
     ap = torch.empty(R, dtype=torch.int64, device="cuda")
     bp = torch.empty(R, M, dtype=torch.float64, device="cuda")
     pred = torch.empty(R, A, dtype=torch.float64, device="cuda")
-    _lib.check(lib.ia2c_belief_update_dense(_lib.ptr(dev(fa)), _lib.ptr(dev(lik)), _lib.ptr(dev(prev)), _lib.ptr(dev(u.reshape(-1))),
+    _lib.check(lib.ia2c_belief_update_dense(dptr((fa)), dptr((lik)), dptr((prev)), dptr((u.reshape(-1))),
                                             _lib.ptr(ap), _lib.ptr(bp), _lib.ptr(pred), R, M, A, _lib.stream_ptr()))
     return host(ap), host(bp), host(pred)
 
@@ -105,7 +105,7 @@ def test_pairs_kernel_vs_oracle(E, N, M):
         pred = torch.empty(E, N, K, dtype=torch.uint8, device="cuda")
         bel = torch.empty(E, N, K, M, dtype=torch.uint8, device="cuda")
         partner = torch.empty(E, N, dtype=torch.uint8, device="cuda")
-        _lib.check(lib.ia2c_belief_update_pairs(_lib.ptr(rec), _lib.ptr(dev(fa)), _lib.ptr(dev(act)), _lib.ptr(dev(u)) if injected else None,
+        _lib.check(lib.ia2c_belief_update_pairs(_lib.ptr(rec), dptr((fa)), dptr((act)), dptr((u)) if injected else None,
                                                 _lib.ptr(pred), _lib.ptr(bel), _lib.ptr(partner), E, N, M, int(t == 0), 77, 5, t, 1000,
                                                 _lib.stream_ptr()))
         oap, obp = _pairs_oracle(fa, act, prior, u)

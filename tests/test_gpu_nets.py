@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 from oracle import nets as NN
-from tests.helpers import dev, host, rel_err
+from tests.helpers import dev, dptr, host, rel_err
 
 pytestmark = pytest.mark.gpu
 RTOL = 1e-5
@@ -62,13 +62,13 @@ def test_mlp_forward_backward_vs_oracle(rows, F, O, softmax):
         x = np.eye(F, dtype=np.float32)[rng.randint(0, F, rows)]
     dy = rng.randn(rows, O).astype(np.float32)
     y = torch.empty(rows, O, device="cuda")
-    _lib.check(lib.ia2c_mlp_forward(_lib.ptr(dev(flat)), _lib.ptr(dev(x)), _lib.ptr(y), rows, F, O, 1, softmax, _lib.stream_ptr()))
+    _lib.check(lib.ia2c_mlp_forward(dptr((flat)), dptr((x)), _lib.ptr(y), rows, F, O, 1, softmax, _lib.stream_ptr()))
     ref, cache = NN.forward(flat.astype(np.float64), x, F, O, softmax=bool(softmax), keep=True)
     assert rel_err(host(y), ref) < RTOL
     grad = torch.full((flat.size,), 7.0, device="cuda")
     dx = torch.empty(rows, F, device="cuda")
     ws = torch.empty(lib.ia2c_mlp_backward_workspace(rows, F, O), device="cuda")
-    _lib.check(lib.ia2c_mlp_backward(_lib.ptr(dev(flat)), _lib.ptr(dev(x)), _lib.ptr(dev(dy)), _lib.ptr(grad), _lib.ptr(dx), _lib.ptr(ws),
+    _lib.check(lib.ia2c_mlp_backward(dptr((flat)), dptr((x)), dptr((dy)), _lib.ptr(grad), _lib.ptr(dx), _lib.ptr(ws),
                                      rows, F, O, softmax, 0, _lib.stream_ptr()))
     dyp = dy.astype(np.float64)
     if softmax:
@@ -79,7 +79,7 @@ def test_mlp_forward_backward_vs_oracle(rows, F, O, softmax):
     dz1 = ((dyp @ NN.unpack(flat.astype(np.float64), F, O)[4]) * (cache[4] > 0)) @ NN.unpack(flat.astype(np.float64), F, O)[2] * (cache[2] > 0)
     assert rel_err(host(dx), dz1 @ W1) < RTOL
     # accumulate mode adds onto the existing gradient
-    _lib.check(lib.ia2c_mlp_backward(_lib.ptr(dev(flat)), _lib.ptr(dev(x)), _lib.ptr(dev(dy)), _lib.ptr(grad), None, _lib.ptr(ws),
+    _lib.check(lib.ia2c_mlp_backward(dptr((flat)), dptr((x)), dptr((dy)), _lib.ptr(grad), None, _lib.ptr(ws),
                                      rows, F, O, softmax, 1, _lib.stream_ptr()))
     assert rel_err(host(grad), 2 * gref) < RTOL
 
@@ -93,7 +93,7 @@ def test_multi_net_forward():
     flat = (rng.randn(nets, 105) * 0.5).astype(np.float32)
     x = rng.randn(rows, 6).astype(np.float32)
     y = torch.empty(nets, rows, 3, device="cuda")
-    _lib.check(lib.ia2c_mlp_forward(_lib.ptr(dev(flat)), _lib.ptr(dev(x)), _lib.ptr(y), rows, 6, 3, nets, 1, _lib.stream_ptr()))
+    _lib.check(lib.ia2c_mlp_forward(dptr((flat)), dptr((x)), _lib.ptr(y), rows, 6, 3, nets, 1, _lib.stream_ptr()))
     for n in range(nets):
         assert rel_err(host(y)[n], NN.forward(flat[n].astype(np.float64), x, 6, 3, softmax=True)) < RTOL
 
@@ -110,14 +110,14 @@ def test_sampler_injected_uniforms_and_philox():
     u = rng.rand(rows).astype(np.float32)
     act = torch.empty(rows, dtype=torch.int64, device="cuda")
     probs = torch.empty(rows, O, device="cuda")
-    _lib.check(lib.ia2c_actor_sample(_lib.ptr(dev(flat)), _lib.ptr(dev(x)), _lib.ptr(dev(u)), _lib.ptr(act), _lib.ptr(probs), rows, F, O, 0, 0, _lib.stream_ptr()))
+    _lib.check(lib.ia2c_actor_sample(dptr((flat)), dptr((x)), dptr((u)), _lib.ptr(act), _lib.ptr(probs), rows, F, O, 0, 0, _lib.stream_ptr()))
     p_ref = NN.forward(flat, x, F, O, softmax=True)
     assert rel_err(host(probs), p_ref) < RTOL
     assert np.array_equal(host(act), NN.sample_inverse_cdf(host(probs).astype(np.float64), u))  # exact given the kernel's own probs
     assert (host(act) != NN.sample_inverse_cdf(p_ref, u)).mean() < 1e-3                          # oracle probs differ by ulps only
     # Philox path: the uniforms are reproducible by the oracle generator
     seed, counter = 1234567, (3 << 16) | 17
-    _lib.check(lib.ia2c_actor_sample(_lib.ptr(dev(flat)), _lib.ptr(dev(x)), None, _lib.ptr(act), _lib.ptr(probs), rows, F, O, seed, counter, _lib.stream_ptr()))
+    _lib.check(lib.ia2c_actor_sample(dptr((flat)), dptr((x)), None, _lib.ptr(act), _lib.ptr(probs), rows, F, O, seed, counter, _lib.stream_ptr()))
     u2 = P.uniform_f32(seed, P.STREAM_ACTION, 3, 17, np.arange(rows))
     assert np.array_equal(host(act), NN.sample_inverse_cdf(host(probs).astype(np.float64), u2))
     freq = np.bincount(host(act), minlength=O) / rows
@@ -150,7 +150,7 @@ def test_adam_matches_oracle_over_many_steps():
     accr = np.zeros_like(p0)
     for it in range(25):
         g = (rng.randn(nets, Pn) * 10 ** rng.uniform(-4, 1)).astype(np.float32)
-        _lib.check(lib.ia2c_adam_step(_lib.ptr(p), _lib.ptr(dev(g)), _lib.ptr(acc), _lib.ptr(m), _lib.ptr(v), _lib.ptr(step),
+        _lib.check(lib.ia2c_adam_step(_lib.ptr(p), dptr((g)), _lib.ptr(acc), _lib.ptr(m), _lib.ptr(v), _lib.ptr(step),
                                       2e-4, 0.9, 0.999, 1e-8, nets, Pn, _lib.stream_ptr()))
         accr = accr + g
         for n in range(nets):

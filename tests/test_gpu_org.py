@@ -3,7 +3,7 @@ import numpy as np
 import pytest
 
 from oracle import org as O
-from tests.helpers import dev, host
+from tests.helpers import dev, dptr, host
 
 pytestmark = pytest.mark.gpu
 
@@ -22,7 +22,7 @@ def _run_joint(s, r, prev, cur, joint, max_steps=0, elapsed=None):
     rew32 = torch.empty(E, device="cuda")
     trace = torch.empty(E, dtype=torch.int32, device="cuda")
     trunc = torch.empty(E, dtype=torch.uint8, device="cuda")
-    _lib.check(lib.ia2c_org_step_joint(_lib.ptr(state), _lib.ptr(hist), _lib.ptr(cls), _lib.ptr(el), _lib.ptr(dev(joint, torch.int32)),
+    _lib.check(lib.ia2c_org_step_joint(_lib.ptr(state), _lib.ptr(hist), _lib.ptr(cls), _lib.ptr(el), dptr(joint, torch.int32),
                                        _lib.ptr(obs), _lib.ptr(rew), _lib.ptr(rew32), _lib.ptr(trace), _lib.ptr(trunc), E, max_steps,
                                        _lib.stream_ptr()))
     torch.cuda.synchronize()

@@ -139,3 +139,32 @@ def test_host_entry_point_matches_device_path():
     ref = b.train_episode(sync_stats=True)
     assert np.array_equal(out["ep_return"], ref["ep_return"]) and np.array_equal(out["critic_loss"], ref["critic_loss"])
     assert np.array_equal(host(a.actor_params), host(b.actor_params))
+
+
+@pytest.mark.parametrize("E,N,M", [(1, 2, 5), (100, 2, 5), (4096, 2, 5), (65, 2, 3), (33, 3, 5), (21, 4, 5), (17, 5, 5), (9, 8, 5)])
+@pytest.mark.parametrize("mode", ["philox", "injected"])
+def test_fused_rollout_is_byte_identical_to_per_step_path(E, N, M, mode):
+    """The persistent one-launch rollout kernel and the per-step kernels must write identical bytes."""
+    T = 30
+    init = _random_init(N, M, seed=N * 7 + M)
+    a = make_trainer(E, N, M, init, seed=5, fused_rollout=False)
+    b = make_trainer(E, N, M, init, seed=5, fused_rollout=True)
+    rng = np.random.RandomState(E)
+    for ep in range(2):
+        if mode == "injected":
+            ua, ub = rng.rand(T + 1, E, N).astype(np.float32), rng.rand(T + 1, E, N, N - 1)
+            a.inject(u_action=ua, u_belief=ub), b.inject(u_action=ua, u_belief=ub)
+        la = a.train_episode(sync_stats=True)
+        lb = b.train_episode(sync_stats=True)
+        for name in ("obs", "reward", "act", "partner_true", "partner_pred", "state_trace", "reward_f64", "pred_dump",
+                     "belief_dump", "belief_records", "env_state", "env_hist", "env_cls", "env_elapsed", "ep_return",
+                     "actor_params", "critic_params", "actor_grad_accum"):
+            assert np.array_equal(host(getattr(a, name)), host(getattr(b, name))), (name, ep)
+        assert np.array_equal(la["critic_loss"], lb["critic_loss"]) and np.array_equal(la["actor_loss"], lb["actor_loss"])
+
+
+def test_fused_rollout_rejects_unsupported_shapes():
+    from ia2c_b200 import _lib
+    tr = make_trainer(4, 9, 5, _random_init(9, 5, seed=1), fused_rollout=True)
+    with pytest.raises(_lib.IA2CError, match="FUSED_ROLLOUT"):
+        tr.train_episode()
