@@ -38,8 +38,9 @@ __device__ __forceinline__ int belief_core(const double* __restrict__ fa, const 
     double S = bp[0];
 #pragma unroll
     for (int m = 1; m < M; ++m) S = __dadd_rn(S, bp[m]);
+    const double rS = drcp_seq(S);   // one refined reciprocal shared by the M divisions (common.cuh)
 #pragma unroll
-    for (int m = 0; m < M; ++m) b[m] = __ddiv_rn(bp[m], S);
+    for (int m = 0; m < M; ++m) b[m] = ddiv_with(bp[m], S, rS);
 #pragma unroll
     for (int a = 0; a < A; ++a) {
         double acc = 0.0;
@@ -79,7 +80,7 @@ belief_dense_kernel(const double* __restrict__ filter_action, const double* __re
     const int ap = belief_core<M, A>(fa, lik, prev, u_in[r], b, pred);
     ap_out[r] = ap;
 #pragma unroll
-    for (int m = 0; m < M; ++m) bprime_out[r * M + m] = __ddiv_rn(rint(__dmul_rn(b[m], 100.0)), 100.0);
+    for (int m = 0; m < M; ++m) bprime_out[r * M + m] = ddiv_seq(rint(__dmul_rn(b[m], 100.0)), 100.0);
     if (pred_out) {
 #pragma unroll
         for (int a = 0; a < A; ++a) pred_out[r * A + a] = pred[a];
@@ -107,8 +108,8 @@ belief_dense_generic_kernel(const double* __restrict__ filter_action, const doub
         S = (m == 0) ? acc : __dadd_rn(S, acc);
     }
     for (int m = 0; m < M; ++m) {
-        b[m] = __ddiv_rn(bp[m], S);
-        bprime_out[r * M + m] = __ddiv_rn(rint(__dmul_rn(b[m], 100.0)), 100.0);
+        b[m] = ddiv_seq(bp[m], S);
+        bprime_out[r * M + m] = ddiv_seq(rint(__dmul_rn(b[m], 100.0)), 100.0);
     }
     const double u = u_in[r];
     double c = 0.0;
@@ -223,6 +224,14 @@ __global__ void __launch_bounds__(kThreads) belief_pairs_kernel(PairsArgs P) {
     }
 }
 
+__global__ void debug_divide_kernel(const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ q_seq,
+                                    double* __restrict__ q_ieee, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    q_seq[i] = ddiv_seq(a[i], b[i]);
+    q_ieee[i] = __ddiv_rn(a[i], b[i]);
+}
+
 template <int M>
 int launch_pairs(PairsArgs& P, cudaStream_t stream) {
     const int64_t per_env = (int64_t)P.N * P.K;
@@ -267,6 +276,12 @@ extern "C" int ia2c_belief_update_dense(const double* filter_action, const doubl
     else if (M == 5 && A == 5) belief_dense_kernel<5, 5><<<blocks, kThreads, 0, s>>>(filter_action, lik, prev, u, ap, bprime, prediction, R);
     else belief_dense_generic_kernel<<<blocks, kThreads, 0, s>>>(filter_action, lik, prev, u, ap, bprime, prediction, R, M, A);
     return check_launch("belief_dense_kernel");
+}
+
+extern "C" int ia2c_debug_divide(const double* a, const double* b, double* q_seq, double* q_ieee, int64_t n, void* stream) {
+    IA2C_REQUIRE(a && b && q_seq && q_ieee && n > 0, "ia2c_debug_divide: null pointer or n=%lld", (long long)n);
+    debug_divide_kernel<<<ceil_div(n, 256), 256, 0, as_stream(stream)>>>(a, b, q_seq, q_ieee, n);
+    return check_launch("debug_divide_kernel");
 }
 
 extern "C" int ia2c_belief_update_pairs(uint8_t* records, const double* filter_action, const uint8_t* actions,

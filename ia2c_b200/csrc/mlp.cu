@@ -141,14 +141,15 @@ actor_sample_kernel(const float* __restrict__ params, const float* __restrict__ 
         float s = 0.f;
 #pragma unroll
         for (int o = 0; o < OMAX; ++o) if (o < O) s += a.y[o];
+        const float us = uu * s;
         float c = 0.f;
         int act = O - 1;
         bool found = false;
 #pragma unroll
         for (int o = 0; o < OMAX; ++o) {
             if (o < O) {
-                c += a.y[o] / s;
-                if (!found && uu < c) { act = o; found = true; }
+                c += a.y[o];
+                if (!found && us < c) { act = o; found = true; }
             }
         }
         if (!WIDE || lane == 0) {

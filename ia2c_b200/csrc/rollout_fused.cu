@@ -152,8 +152,9 @@ __global__ void __launch_bounds__(kThreads) rollout_fused_kernel(ia2c_episode_de
             double S = bp[0];
 #pragma unroll
             for (int m = 1; m < M; ++m) S = __dadd_rn(S, bp[m]);
+            const double rS = drcp_seq(S);
 #pragma unroll
-            for (int m = 0; m < M; ++m) b[m] = __ddiv_rn(bp[m], S);
+            for (int m = 0; m < M; ++m) b[m] = ddiv_with(bp[m], S, rS);
 #pragma unroll
             for (int k = 0; k < A; ++k) {
                 double acc = 0.0;

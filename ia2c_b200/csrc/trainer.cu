@@ -157,13 +157,145 @@ __device__ __forceinline__ void load_obs(const float* __restrict__ p, float (&x)
     x[0] = a.x; x[1] = a.y; x[2] = b.x; x[3] = b.y; x[4] = c.x; x[5] = c.y;
 }
 
+// ---- shared-memory weights for the gradient kernels -----------------------------------------------
+// At hidden_size 6 every FFMA needs one weight, and a 32-bit broadcast LDS per FFMA makes the kernels
+// LSU-bound (one shared-memory wavefront per cycle per SM; measured, profiles/).  The weights are
+// therefore staged in a PADDED layout — every 6-wide row padded to 8 floats — so a row is fetched by
+// two 128-bit broadcast loads, and each fetched row is used for NX inputs at once (obs and next_obs).
+template <int O>
+struct PadLayout {
+    static constexpr int w1 = 0, b1 = 48, w2 = 56, b2 = 104, w3 = 112, b3 = 112 + O * 8, size = b3 + ((O + 3) / 4) * 4;
+};
+
+template <int O>
+__device__ __forceinline__ void stage_padded(float* sw, const float* __restrict__ flat) {
+    using L = PadLayout<O>;
+    using D = MlpDims<F, O>;
+    for (int i = threadIdx.x; i < L::size; i += blockDim.x) {
+        float v = 0.f;
+        const int r = (i - 0) / 8, c = i % 8;
+        if (i < L::b1) { if (c < F) v = flat[D::w1 + r * F + c]; }
+        else if (i < L::w2) { if (i - L::b1 < H) v = flat[D::b1 + i - L::b1]; }
+        else if (i < L::b2) { const int rr = (i - L::w2) / 8; if (c < H) v = flat[D::w2 + rr * H + c]; }
+        else if (i < L::w3) { if (i - L::b2 < H) v = flat[D::b2 + i - L::b2]; }
+        else if (i < L::b3) { const int rr = (i - L::w3) / 8; if (c < H) v = flat[D::w3 + rr * H + c]; }
+        else { if (i - L::b3 < O) v = flat[D::b3 + i - L::b3]; }
+        sw[i] = v;
+    }
+}
+
+__device__ __forceinline__ void row8(const float* p, float (&r)[8]) {
+    const float4 a = *reinterpret_cast<const float4*>(p);
+    const float4 b = *reinterpret_cast<const float4*>(p + 4);
+    r[0] = a.x; r[1] = a.y; r[2] = a.z; r[3] = a.w; r[4] = b.x; r[5] = b.y; r[6] = b.z; r[7] = b.w;
+}
+
+// Forward of NX inputs through one network; each weight row is fetched once for all NX inputs.
+template <int O, int NX>
+__device__ __forceinline__ void fwd_padded(const float* sw, const float (&x)[NX][F], float (&h1)[NX][H],
+                                           float (&h2)[NX][H], float (&y)[NX][O]) {
+    using L = PadLayout<O>;
+    float r[8], bias[8];
+    row8(sw + L::b1, bias);
+#pragma unroll
+    for (int j = 0; j < H; ++j) {
+        row8(sw + L::w1 + j * 8, r);
+#pragma unroll
+        for (int n = 0; n < NX; ++n) {
+            float acc = bias[j];
+#pragma unroll
+            for (int f = 0; f < F; ++f) acc = fmaf(r[f], x[n][f], acc);
+            h1[n][j] = fmaxf(acc, 0.f);
+        }
+    }
+    row8(sw + L::b2, bias);
+#pragma unroll
+    for (int j = 0; j < H; ++j) {
+        row8(sw + L::w2 + j * 8, r);
+#pragma unroll
+        for (int n = 0; n < NX; ++n) {
+            float acc = bias[j];
+#pragma unroll
+            for (int k = 0; k < H; ++k) acc = fmaf(r[k], h1[n][k], acc);
+            h2[n][j] = fmaxf(acc, 0.f);
+        }
+    }
+#pragma unroll
+    for (int o = 0; o < O; ++o) {
+        row8(sw + L::w3 + o * 8, r);
+        const float bo = sw[L::b3 + o];
+#pragma unroll
+        for (int n = 0; n < NX; ++n) {
+            float acc = bo;
+#pragma unroll
+            for (int k = 0; k < H; ++k) acc = fmaf(r[k], h2[n][k], acc);
+            y[n][o] = acc;
+        }
+    }
+}
+
+// Backward of NX inputs (dy wrt the pre-softmax outputs), accumulating into g (flat MlpDims layout).
+// dy(n, o) is a callable so that sparse output gradients (the critic's single selected Q) need no array.
+template <int O, int NX, int GN, typename DY>
+__device__ __forceinline__ void bwd_padded(const float* sw, const float (&x)[NX][F], const float (&h1)[NX][H],
+                                           const float (&h2)[NX][H], DY dy, float (&g)[GN]) {
+    using L = PadLayout<O>;
+    using D = MlpDims<F, O>;
+    static_assert(GN >= D::P, "gradient accumulator too small");
+    float r[8];
+    float dh2[NX][H], dh1[NX][H];
+#pragma unroll
+    for (int n = 0; n < NX; ++n)
+#pragma unroll
+        for (int k = 0; k < H; ++k) dh2[n][k] = dh1[n][k] = 0.f;
+#pragma unroll
+    for (int o = 0; o < O; ++o) {
+        row8(sw + L::w3 + o * 8, r);
+#pragma unroll
+        for (int n = 0; n < NX; ++n) {
+            const float dyv = dy(n, o);
+            g[D::b3 + o] += dyv;
+#pragma unroll
+            for (int k = 0; k < H; ++k) {
+                g[D::w3 + o * H + k] = fmaf(dyv, h2[n][k], g[D::w3 + o * H + k]);
+                dh2[n][k] = fmaf(dyv, r[k], dh2[n][k]);
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < H; ++j) {
+        row8(sw + L::w2 + j * 8, r);
+#pragma unroll
+        for (int n = 0; n < NX; ++n) {
+            const float dz = h2[n][j] > 0.f ? dh2[n][j] : 0.f;
+            g[D::b2 + j] += dz;
+#pragma unroll
+            for (int k = 0; k < H; ++k) {
+                g[D::w2 + j * H + k] = fmaf(dz, h1[n][k], g[D::w2 + j * H + k]);
+                dh1[n][k] = fmaf(dz, r[k], dh1[n][k]);
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < H; ++j) {
+#pragma unroll
+        for (int n = 0; n < NX; ++n) {
+            const float dz = h1[n][j] > 0.f ? dh1[n][j] : 0.f;
+            g[D::b1 + j] += dz;
+#pragma unroll
+            for (int f = 0; f < F; ++f) g[D::w1 + j * F + f] = fmaf(dz, x[n][f], g[D::w1 + j * F + f]);
+        }
+    }
+}
+
 // partial row layout: P gradient entries then the loss partial.
 __global__ void __launch_bounds__(kGradThreads) critic_grad_kernel(ia2c_episode_desc d, float* __restrict__ partials) {
     constexpr int P = kCriticP;
-    __shared__ float w[P];
+    __shared__ __align__(16) float w[PadLayout<J>::size];
     __shared__ float red[(kGradThreads / 32) * (P + 1)];
     const int n = blockIdx.y, N = d.N;
-    for (int i = threadIdx.x; i < P; i += blockDim.x) w[i] = d.critic_params[(int64_t)n * P + i];
+    stage_padded<J>(w, d.critic_params + (int64_t)n * P);
+    if (blockIdx.x == 0 && threadIdx.x == 0 && !(d.flags & IA2C_FLAG_SKIP_ADAM)) d.critic_step[n] += 1;
     __syncthreads();
     const int64_t E = d.E, rows = (int64_t)d.T * E;
     const float inv_b = 1.f / (float)((int64_t)d.T * d.E_total);
@@ -171,45 +303,66 @@ __global__ void __launch_bounds__(kGradThreads) critic_grad_kernel(ia2c_episode_
 #pragma unroll
     for (int i = 0; i <= P; ++i) g[i] = 0.f;
     for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x) {
-        float x[F], xn[F], h1[H], h2[H], q[J], h1n[H], h2n[H], qn[J];
-        load_obs(d.obs + r * F, x);
-        load_obs(d.obs + (r + E) * F, xn);                       // next_obs[t] = obs[t+1]
-        mlp_forward<F, J>(w, x, h1, h2, q);
-        mlp_forward<F, J>(w, xn, h1n, h2n, qn);
+        float x[2][F];
+        load_obs(d.obs + r * F, x[0]);
+        load_obs(d.obs + (r + E) * F, x[1]);                     // next_obs[t] = obs[t+1]
         const int own = d.act[r * N + n], own_n = d.act[(r + E) * N + n];
         const int jt = joint_index(n, N, own, d.partner_true[r * N + n]);            // ia2c.py:112
         const int nja = joint_index(n, N, own_n, d.partner_pred[(r + E) * N + n]);   // ia2c.py:104-105
         float qsel = 0.f, qnsel = 0.f;
+        // One pass at a time (and activations recomputed for the backward below): with 148 gradient
+        // accumulators per thread the register file, not the FMA pipe, is the scarce resource.
+        {
+            float x1[1][F], h1[1][H], h2[1][H], q1[1][J];
 #pragma unroll
-        for (int o = 0; o < J; ++o) {
-            qsel = (o == jt) ? q[o] : qsel;
-            qnsel = (o == nja) ? qn[o] : qnsel;
+            for (int f = 0; f < F; ++f) x1[0][f] = x[0][f];
+            fwd_padded<J, 1>(w, x1, h1, h2, q1);
+#pragma unroll
+            for (int o = 0; o < J; ++o) qsel = (o == jt) ? q1[0][o] : qsel;
+        }
+        {
+            float x1[1][F], h1[1][H], h2[1][H], q1[1][J];
+#pragma unroll
+            for (int f = 0; f < F; ++f) x1[0][f] = x[1][f];
+            fwd_padded<J, 1>(w, x1, h1, h2, q1);
+#pragma unroll
+            for (int o = 0; o < J; ++o) qnsel = (o == nja) ? q1[0][o] : qnsel;
         }
         const float target = d.reward[r] + d.gamma * qnsel;      // ia2c.py:110 (graph attached, Q8)
         const float delta = target - qsel;
         if (d.target_dump) d.target_dump[(int64_t)n * rows + r] = target;
         g[P] = fmaf(delta, delta, g[P]);
-        const float gq = -2.f * delta * inv_b;
-        float dy[J];
+        const float gq = -2.f * delta * inv_b;                   // dL/dQ(obs)[jt]
+        const float gqn = 2.f * d.gamma * delta * inv_b;         // dL/dQ(next_obs)[nja]: residual gradient
+        // Backward through each pass in turn, recomputing its activations: 252 extra FFMA per row buy ~40
+        // fewer live registers next to the 148 gradient accumulators (no local-memory spills).
+        {
+            float x1[1][F], h1[1][H], h2[1][H], q1[1][J];
 #pragma unroll
-        for (int o = 0; o < J; ++o) dy[o] = (o == jt) ? gq : 0.f;
-        mlp_backward_accum<F, J>(w, x, h1, h2, dy, g);
-        const float gqn = 2.f * d.gamma * delta * inv_b;
+            for (int f = 0; f < F; ++f) { x1[0][f] = x[0][f]; asm volatile("" : "+f"(x1[0][f])); }   // opaque: defeat CSE with the paired forward
+            fwd_padded<J, 1>(w, x1, h1, h2, q1);
+            bwd_padded<J, 1>(w, x1, h1, h2, [&](int, int o) { return o == jt ? gq : 0.f; }, g);
+        }
+        {
+            float x1[1][F], h1[1][H], h2[1][H], q1[1][J];
 #pragma unroll
-        for (int o = 0; o < J; ++o) dy[o] = (o == nja) ? gqn : 0.f;
-        mlp_backward_accum<F, J>(w, xn, h1n, h2n, dy, g);
+            for (int f = 0; f < F; ++f) { x1[0][f] = x[1][f]; asm volatile("" : "+f"(x1[0][f])); }
+            fwd_padded<J, 1>(w, x1, h1, h2, q1);
+            bwd_padded<J, 1>(w, x1, h1, h2, [&](int, int o) { return o == nja ? gqn : 0.f; }, g);
+        }
     }
     block_reduce_store<P + 1>(g, red, partials + ((int64_t)n * gridDim.x + blockIdx.x) * (P + 1));
 }
 
 __global__ void __launch_bounds__(kGradThreads) actor_grad_kernel(ia2c_episode_desc d, float* __restrict__ partials) {
     constexpr int P = kActorP, PC = kCriticP;
-    __shared__ float wc[PC];
-    __shared__ float w[P];
+    __shared__ __align__(16) float wc[PadLayout<J>::size];
+    __shared__ __align__(16) float w[PadLayout<A>::size];
     __shared__ float red[(kGradThreads / 32) * (P + 1)];
     const int n = blockIdx.y, N = d.N;
-    for (int i = threadIdx.x; i < PC; i += blockDim.x) wc[i] = d.critic_params[(int64_t)n * PC + i];
-    for (int i = threadIdx.x; i < P; i += blockDim.x) w[i] = d.actor_params[(int64_t)n * P + i];
+    stage_padded<J>(wc, d.critic_params + (int64_t)n * PC);
+    stage_padded<A>(w, d.actor_params + (int64_t)n * P);
+    if (blockIdx.x == 0 && threadIdx.x == 0 && !(d.flags & IA2C_FLAG_SKIP_ADAM)) d.actor_step[n] += 1;
     __syncthreads();
     const int64_t E = d.E, rows = (int64_t)d.T * E;
     const float inv_b = 1.f / (float)((int64_t)d.T * d.E_total);
@@ -217,28 +370,30 @@ __global__ void __launch_bounds__(kGradThreads) actor_grad_kernel(ia2c_episode_d
 #pragma unroll
     for (int i = 0; i <= P; ++i) g[i] = 0.f;
     for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x) {
-        float x[F], xn[F], h1[H], h2[H];
-        load_obs(d.obs + r * F, x);
-        load_obs(d.obs + (r + E) * F, xn);
+        float x[2][F];
+        load_obs(d.obs + r * F, x[0]);
+        load_obs(d.obs + (r + E) * F, x[1]);
         const int own = d.act[r * N + n], own_n = d.act[(r + E) * N + n];
         const int ja = joint_index(n, N, own, d.partner_pred[r * N + n]);            // ia2c.py:120-121
         const int nja = joint_index(n, N, own_n, d.partner_pred[(r + E) * N + n]);
         float adv;
         {   // advantage from the UPDATED critic, no gradient (ia2c.py:116-127)
-            float q[J], qn[J];
-            mlp_forward<F, J>(wc, x, h1, h2, q);
-            mlp_forward<F, J>(wc, xn, h1, h2, qn);
+            float h1[2][H], h2[2][H], q[2][J];
+            fwd_padded<J, 2>(wc, x, h1, h2, q);
             float qsel = 0.f, qnsel = 0.f;
 #pragma unroll
             for (int o = 0; o < J; ++o) {
-                qsel = (o == ja) ? q[o] : qsel;
-                qnsel = (o == nja) ? qn[o] : qnsel;
+                qsel = (o == ja) ? q[0][o] : qsel;
+                qnsel = (o == nja) ? q[1][o] : qnsel;
             }
             adv = (d.reward[r] + d.gamma * qnsel) - qsel;
         }
         if (d.adv_dump) d.adv_dump[(int64_t)n * rows + r] = adv;
-        float p[A];
-        mlp_forward<F, A>(w, x, h1, h2, p);
+        float x1[1][F], h1[1][H], h2[1][H], pp[1][A];
+#pragma unroll
+        for (int f = 0; f < F; ++f) x1[0][f] = x[0][f];
+        fwd_padded<A, 1>(w, x1, h1, h2, pp);
+        float (&p)[A] = pp[0];
         softmax_inplace<A>(p);
         // Categorical(probs=p): q = p/sum(p); logit = log(clamp(q)); loss_row = adv*(-logit[a]) - beta*H
         float s = 0.f;
@@ -264,7 +419,7 @@ __global__ void __launch_bounds__(kGradThreads) actor_grad_kernel(ia2c_episode_d
         float dy[A];
 #pragma unroll
         for (int o = 0; o < A; ++o) dy[o] = qq[o] * (gq[o] - qg) * inv_b;   // through normalise + softmax
-        mlp_backward_accum<F, A>(w, x, h1, h2, dy, g);
+        bwd_padded<A, 1>(w, x1, h1, h2, [&](int, int o) { return dy[o]; }, g);
     }
     block_reduce_store<P + 1>(g, red, partials + ((int64_t)n * gridDim.x + blockIdx.x) * (P + 1));
 }
@@ -276,7 +431,7 @@ struct ReduceArgs {
     float* grad;            // [N, P+1]
     float* grad_accum;      // [N, P] or null
     float* params; float* m; float* v;
-    int32_t* step;          // [N], incremented here when apply_adam
+    int32_t* step;          // [N], already incremented for this update
     float* loss_out;        // [N]
     float loss_scale;       // 1 / (T * E_total)
     double lr;
@@ -294,45 +449,56 @@ __device__ __forceinline__ void adam_update(float& p, float& m, float& v, float 
     p = p - step_size * (mi / (sqrtf(vi) / bc2_sqrt + 1e-8f));
 }
 
+// grid (N, ceil((P+1)/32)); block 256 = 32 entries x 8 slices of the partial blocks; fixed-order sums.
 __global__ void __launch_bounds__(256) reduce_adam_kernel(ReduceArgs R) {
     const int n = blockIdx.x, P = R.P;
-    __shared__ int t_shared;
-    if (threadIdx.x == 0) t_shared = R.step[n] + 1;
-    __syncthreads();
-    const int t = t_shared;
-    for (int i = threadIdx.x; i <= P; i += blockDim.x) {
-        float s;
+    const int col = threadIdx.x & 31, slice = threadIdx.x >> 5;
+    const int i = blockIdx.y * 32 + col;
+    __shared__ float part[8][33];
+    float s = 0.f;
+    if (i <= P) {
         if (R.from_partials) {
-            s = 0.f;
             const float* src = R.partials + (int64_t)n * R.n_blocks * (P + 1) + i;
-            for (int b = 0; b < R.n_blocks; ++b) s += src[(int64_t)b * (P + 1)];
-            if (i == P) s *= R.loss_scale;
-            R.grad[(int64_t)n * (P + 1) + i] = s;
-        } else {
+            for (int b = slice; b < R.n_blocks; b += 8) s += src[(int64_t)b * (P + 1)];
+        } else if (slice == 0) {
             s = R.grad[(int64_t)n * (P + 1) + i];
         }
-        if (i == P) {
-            R.loss_out[n] = s;
-        } else if (R.apply_adam) {
-            const int64_t k = (int64_t)n * P + i;
-            float g = s;
-            if (R.grad_accum) {          // the reference's actor never zeroes its gradients (Q2)
-                g += R.grad_accum[k];
-                R.grad_accum[k] = g;
-            }
-            adam_update(R.params[k], R.m[k], R.v[k], g, t, R.lr);
-        }
     }
+    part[slice][col] = s;
     __syncthreads();
-    if (R.apply_adam && threadIdx.x == 0) R.step[n] = t;
+    if (slice != 0 || i > P) return;
+#pragma unroll
+    for (int k = 1; k < 8; ++k) s += part[k][col];
+    if (R.from_partials) {
+        if (i == P) s *= R.loss_scale;
+        R.grad[(int64_t)n * (P + 1) + i] = s;
+    }
+    if (i == P) {
+        R.loss_out[n] = s;
+    } else if (R.apply_adam) {
+        const int t = R.step[n];             // already incremented by the gradient kernel / apply entry
+        const int64_t k = (int64_t)n * P + i;
+        float g = s;
+        if (R.grad_accum) {                  // the reference's actor never zeroes its gradients (Q2)
+            g += R.grad_accum[k];
+            R.grad_accum[k] = g;
+        }
+        adam_update(R.params[k], R.m[k], R.v[k], g, t, R.lr);
+    }
 }
 
+__global__ void bump_steps_kernel(int32_t* step, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) step[i] += 1;
+}
+
+// Blocks per agent for the gradient kernels: one resident wave (2 blocks of 128 threads per SM at 255
+// registers) shared by the N agents, grid-stride over the rows, but never fewer than ~4 rows per thread.
 int grad_blocks(const ia2c_episode_desc* d) {
     const int64_t rows = (int64_t)d->T * d->E;
-    int64_t b = (rows + kGradThreads * 2 - 1) / (kGradThreads * 2);   // ~2 rows per thread
-    const int64_t cap = std::max<int64_t>(1, (int64_t)kSMs * 8 / std::max(1, d->N));
-    b = std::min<int64_t>(b, std::max<int64_t>(cap, 8));
-    return (int)std::max<int64_t>(1, b);
+    const int64_t by_rows = (rows + kGradThreads * 4 - 1) / (kGradThreads * 4);
+    const int64_t by_wave = std::max<int64_t>(1, (int64_t)kSMs * 2 / std::max(1, d->N));
+    return (int)std::max<int64_t>(1, std::min(by_rows, by_wave));
 }
 
 int validate(const ia2c_episode_desc* d, const char* who) {
@@ -411,7 +577,12 @@ static int run_reduce(const ia2c_episode_desc* d, int which, int from_partials, 
     R.lr = which == 0 ? d->lr_critic : d->lr_actor;
     R.apply_adam = apply;
     R.from_partials = from_partials;
-    reduce_adam_kernel<<<d->N, 256, 0, s>>>(R);
+    if (!from_partials && apply) {   // ia2c_apply_adam: the gradient kernel did not bump the step counter
+        bump_steps_kernel<<<ceil_div(d->N, 256), 256, 0, s>>>(R.step, d->N);
+        if (int rc = check_launch("bump_steps_kernel")) return rc;
+    }
+    dim3 grid(d->N, ceil_div(R.P + 1, 32));
+    reduce_adam_kernel<<<grid, 256, 0, s>>>(R);
     return check_launch("reduce_adam_kernel");
 }
 

@@ -101,6 +101,11 @@ int ia2c_belief_update_pairs(uint8_t* records, const double* filter_action, cons
                              uint8_t* pred_partner_out, int64_t E, int32_t N, int32_t M, int32_t reset_prior,
                              uint64_t seed, uint32_t episode, uint32_t t, int64_t env_offset, void* stream);
 
+/* Diagnostic: q_seq[i] = the library's branch-free fp64 division sequence (csrc/common.cuh: ddiv_seq),
+ * q_ieee[i] = IEEE a/b (__ddiv_rn).  Used by the tests to prove the two agree bit for bit on the
+ * operand ranges the belief filter and the reward recurrence produce. */
+int ia2c_debug_divide(const double* a, const double* b, double* q_seq, double* q_ieee, int64_t n, void* stream);
+
 /* ------------------------------------------------------------------ (3) actor / critic MLPs -- */
 /* NeuralNet.forward (ac_nets.py:34-41) for `nets` independent networks over the same rows:
  *   params float[nets,P]; x float[rows,F] (shared by all nets) -> y float[nets,rows,O];

@@ -164,11 +164,20 @@ class AdamRef:
 
 def sample_inverse_cdf(probs, u):
     """Performance-mode action sampler of the CUDA path (NOT the reference's torch.multinomial stream):
-    q = p/sum(p); first k with u < cumsum(q)[k]; none -> last index."""
+    q = p/sum(p) (Categorical renormalises); first k with u*sum(p) < cumsum(p)[k]; none -> last index.
+    Sequential sums in the dtype of ``probs``, like the kernel."""
     p = np.asarray(probs)
-    q = p / p.sum(-1, keepdims=True)
-    c = np.cumsum(q, axis=-1, dtype=q.dtype)
-    hit = np.asarray(u).reshape(-1, 1) < c
-    k = hit.argmax(-1)
-    k[~hit.any(-1)] = p.shape[-1] - 1
-    return k
+    dt = p.dtype
+    s = np.zeros(p.shape[:-1], dtype=dt)
+    for k in range(p.shape[-1]):
+        s = (s + p[..., k]).astype(dt)
+    us = (np.asarray(u, dtype=dt).reshape(s.shape) * s).astype(dt)
+    c = np.zeros_like(s)
+    out = np.full(s.shape, p.shape[-1] - 1, dtype=np.int64)
+    found = np.zeros(s.shape, dtype=bool)
+    for k in range(p.shape[-1]):
+        c = (c + p[..., k]).astype(dt)
+        hit = (~found) & (us < c)
+        out[hit] = k
+        found |= hit
+    return out

@@ -113,13 +113,13 @@ def test_sampler_injected_uniforms_and_philox():
     _lib.check(lib.ia2c_actor_sample(dptr((flat)), dptr((x)), dptr((u)), _lib.ptr(act), _lib.ptr(probs), rows, F, O, 0, 0, _lib.stream_ptr()))
     p_ref = NN.forward(flat, x, F, O, softmax=True)
     assert rel_err(host(probs), p_ref) < RTOL
-    assert np.array_equal(host(act), NN.sample_inverse_cdf(host(probs).astype(np.float64), u))  # exact given the kernel's own probs
+    assert np.array_equal(host(act), NN.sample_inverse_cdf(host(probs), u))  # exact given the kernel's own probs
     assert (host(act) != NN.sample_inverse_cdf(p_ref, u)).mean() < 1e-3                          # oracle probs differ by ulps only
     # Philox path: the uniforms are reproducible by the oracle generator
     seed, counter = 1234567, (3 << 16) | 17
     _lib.check(lib.ia2c_actor_sample(dptr((flat)), dptr((x)), None, _lib.ptr(act), _lib.ptr(probs), rows, F, O, seed, counter, _lib.stream_ptr()))
     u2 = P.uniform_f32(seed, P.STREAM_ACTION, 3, 17, np.arange(rows))
-    assert np.array_equal(host(act), NN.sample_inverse_cdf(host(probs).astype(np.float64), u2))
+    assert np.array_equal(host(act), NN.sample_inverse_cdf(host(probs), u2))
     freq = np.bincount(host(act), minlength=O) / rows
     assert np.abs(freq - host(probs).mean(0)).max() < 0.02
 
