@@ -19,6 +19,7 @@ import torch.nn as nn
 
 from . import _lib
 from .nets import hidden_size
+from .sharding import shard_envs
 
 N_FEATURES, N_ACTIONS, N_JOINT = 6, 3, 9
 
@@ -53,10 +54,8 @@ class IA2CTrainer:
         self.lib = _lib.load()
         self.rank, self.world = int(rank), int(world_size)
         self.pg = process_group
-        if num_envs % self.world:
-            raise ValueError("num_envs must be divisible by world_size (envs are sharded across ranks)")
         self.E_total = int(num_envs)
-        self.E = self.E_total // self.world
+        self.env_offset, self.E = shard_envs(self.E_total, self.rank, self.world)
         self.N, self.M, self.T = int(n_agents), int(n_models), int(steps_per_episode)
         self.K = self.N - 1
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
@@ -90,7 +89,7 @@ class IA2CTrainer:
             self.adv_dump, self.target_dump = z((N, T, E), f32), z((N, T, E), f32)
         self.desc = _lib.EpisodeDesc()
         d = self.desc
-        d.E, d.E_total, d.env_offset = E, self.E_total, self.rank * E
+        d.E, d.E_total, d.env_offset = E, self.E_total, self.env_offset
         d.N, d.T, d.M, d.max_episode_steps = N, T, M, int(max_episode_steps or 0)
         d.gamma, d.beta, d.lr_actor, d.lr_critic = gamma, beta, lr_actor, lr_critic
         d.seed, d.episode = self.seed, 0
