@@ -28,6 +28,9 @@ if ROOT not in sys.path:
 METRIC = "agent-steps/sec incl. A2C update (Org domain)"
 UNIT = "agent-steps/s"
 T_STEPS, N_MODELS = 30, 5
+# dram__bytes_read.sum + dram__bytes_write.sum of rollout_fused_kernel<2,5> per launch, from the ncu --set full
+# capture summarised in profiles/r01_ncu_full_summary.md (the 4.5 MB trajectory it writes stays in the 126 MB L2)
+NCU_ROLLOUT_DRAM_BYTES = 24576
 
 
 def parse():
@@ -381,7 +384,7 @@ def run_ours(args):
                        "IA2CTrainer.inject(copy from pinned) + train_episode(sync_stats=True)"},
         "gpu_launches": int(launches),
         "roofline": {"kernel": kname, "bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
-                     "traffic": None, "bytes_per_launch": traj_bytes, "us_per_launch": rollout_us,
+                     "traffic": NCU_ROLLOUT_DRAM_BYTES if (fused and N == 2 and E_gpu == 4096) else None, "bytes_per_launch": traj_bytes, "us_per_launch": rollout_us,
                      "share_of_step": rollout_ms / step_ms,
                      "note": "latency-bound by construction: 31 sequential steps per env and only E*N = 8192 threads; "
                              "HBM-bound streaming kernels are reported under 'kernels'"},
