@@ -288,6 +288,33 @@ __device__ __forceinline__ void bwd_padded(const float* sw, const float (&x)[NX]
     }
 }
 
+// ---- gradient kernels: one thread per (agent, env, time chunk) ---------------------------------------
+// next_obs[t] IS obs[t+1] (trajectory layout), so a thread that walks a chunk [t0,t1) of one env's
+// time axis evaluates the critic ONCE per observation (L+1 forwards for L rows instead of 2L) and, in the
+// critic phase, back-propagates ONCE per observation with the two output-gradient contributions it
+// receives — as Q(obs_t)[jt_t] of row t and as the bootstrap Q(next_obs_{t-1})[nja_{t-1}] of row t-1 —
+// added together first (L+1 backward passes instead of 2L).  Same sums, fewer passes.
+struct ChunkPlan { int chunk_len, n_chunks; };
+__host__ __device__ inline ChunkPlan chunk_plan(int T, int64_t E, int N) {
+    // enough (env, chunk) items per agent for one resident wave of 148 SMs x 2 blocks x 128 threads over N agents
+    const int64_t target = (int64_t)kSMs * 2 * 128;
+    int64_t c = target / (E * N);   // floor: all items must fit in ONE pass of the resident wave
+    if (c < 1) c = 1;
+    if (c > T) c = T;
+    ChunkPlan p;
+    p.chunk_len = (int)((T + c - 1) / c);
+    p.n_chunks = (T + p.chunk_len - 1) / p.chunk_len;
+    return p;
+}
+
+template <int O>
+__device__ __forceinline__ float select_q(const float (&q)[1][O], int idx) {
+    float v = 0.f;
+#pragma unroll
+    for (int o = 0; o < O; ++o) v = (o == idx) ? q[0][o] : v;
+    return v;
+}
+
 // partial row layout: P gradient entries then the loss partial.
 __global__ void __launch_bounds__(kGradThreads) critic_grad_kernel(ia2c_episode_desc d, float* __restrict__ partials) {
     constexpr int P = kCriticP;
@@ -298,58 +325,46 @@ __global__ void __launch_bounds__(kGradThreads) critic_grad_kernel(ia2c_episode_
     if (blockIdx.x == 0 && threadIdx.x == 0 && !(d.flags & IA2C_FLAG_SKIP_ADAM)) d.critic_step[n] += 1;
     __syncthreads();
     const int64_t E = d.E, rows = (int64_t)d.T * E;
+    const ChunkPlan cp = chunk_plan(d.T, E, N);
+    const int64_t items = E * cp.n_chunks;
     const float inv_b = 1.f / (float)((int64_t)d.T * d.E_total);
     float g[P + 1];
 #pragma unroll
     for (int i = 0; i <= P; ++i) g[i] = 0.f;
-    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x) {
-        float x[2][F];
-        load_obs(d.obs + r * F, x[0]);
-        load_obs(d.obs + (r + E) * F, x[1]);                     // next_obs[t] = obs[t+1]
-        const int own = d.act[r * N + n], own_n = d.act[(r + E) * N + n];
-        const int jt = joint_index(n, N, own, d.partner_true[r * N + n]);            // ia2c.py:112
-        const int nja = joint_index(n, N, own_n, d.partner_pred[(r + E) * N + n]);   // ia2c.py:104-105
-        float qsel = 0.f, qnsel = 0.f;
-        // One pass at a time (and activations recomputed for the backward below): with 148 gradient
-        // accumulators per thread the register file, not the FMA pipe, is the scarce resource.
-        {
-            float x1[1][F], h1[1][H], h2[1][H], q1[1][J];
+    for (int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; item < items; item += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t e = item % E;
+        const int t0 = (int)(item / E) * cp.chunk_len;
+        const int t1 = min(d.T, t0 + cp.chunk_len);
+        float x[1][F], h1[1][H], h2[1][H], q[1][J];
+        load_obs(d.obs + ((int64_t)t0 * E + e) * F, x[0]);
+        fwd_padded<J, 1>(w, x, h1, h2, q);
+        int carry_idx = -1;          // pending bootstrap gradient for the CURRENT observation (from row t-1)
+        float carry_val = 0.f;
+        for (int t = t0; t < t1; ++t) {
+            const int64_t r = (int64_t)t * E + e;
+            float xn[1][F], h1n[1][H], h2n[1][H], qn[1][J];
+            load_obs(d.obs + (r + E) * F, xn[0]);                    // next_obs[t] = obs[t+1]
+            fwd_padded<J, 1>(w, xn, h1n, h2n, qn);
+            const int own = d.act[r * N + n], own_n = d.act[(r + E) * N + n];
+            const int jt = joint_index(n, N, own, d.partner_true[r * N + n]);            // ia2c.py:112
+            const int nja = joint_index(n, N, own_n, d.partner_pred[(r + E) * N + n]);   // ia2c.py:104-105
+            const float target = d.reward[r] + d.gamma * select_q<J>(qn, nja);           // ia2c.py:110 (Q8)
+            const float delta = target - select_q<J>(q, jt);
+            if (d.target_dump) d.target_dump[(int64_t)n * rows + r] = target;
+            g[P] = fmaf(delta, delta, g[P]);
+            const float gq = -2.f * delta * inv_b;                   // dL/dQ(obs_t)[jt]
+            bwd_padded<J, 1>(w, x, h1, h2,
+                             [&](int, int o) { return (o == jt ? gq : 0.f) + (o == carry_idx ? carry_val : 0.f); }, g);
+            carry_idx = nja;
+            carry_val = 2.f * d.gamma * delta * inv_b;               // dL/dQ(next_obs_t)[nja]: residual gradient
 #pragma unroll
-            for (int f = 0; f < F; ++f) x1[0][f] = x[0][f];
-            fwd_padded<J, 1>(w, x1, h1, h2, q1);
+            for (int k = 0; k < F; ++k) x[0][k] = xn[0][k];
 #pragma unroll
-            for (int o = 0; o < J; ++o) qsel = (o == jt) ? q1[0][o] : qsel;
+            for (int k = 0; k < H; ++k) { h1[0][k] = h1n[0][k]; h2[0][k] = h2n[0][k]; }
+#pragma unroll
+            for (int o = 0; o < J; ++o) q[0][o] = qn[0][o];
         }
-        {
-            float x1[1][F], h1[1][H], h2[1][H], q1[1][J];
-#pragma unroll
-            for (int f = 0; f < F; ++f) x1[0][f] = x[1][f];
-            fwd_padded<J, 1>(w, x1, h1, h2, q1);
-#pragma unroll
-            for (int o = 0; o < J; ++o) qnsel = (o == nja) ? q1[0][o] : qnsel;
-        }
-        const float target = d.reward[r] + d.gamma * qnsel;      // ia2c.py:110 (graph attached, Q8)
-        const float delta = target - qsel;
-        if (d.target_dump) d.target_dump[(int64_t)n * rows + r] = target;
-        g[P] = fmaf(delta, delta, g[P]);
-        const float gq = -2.f * delta * inv_b;                   // dL/dQ(obs)[jt]
-        const float gqn = 2.f * d.gamma * delta * inv_b;         // dL/dQ(next_obs)[nja]: residual gradient
-        // Backward through each pass in turn, recomputing its activations: 252 extra FFMA per row buy ~40
-        // fewer live registers next to the 148 gradient accumulators (no local-memory spills).
-        {
-            float x1[1][F], h1[1][H], h2[1][H], q1[1][J];
-#pragma unroll
-            for (int f = 0; f < F; ++f) { x1[0][f] = x[0][f]; asm volatile("" : "+f"(x1[0][f])); }   // opaque: defeat CSE with the paired forward
-            fwd_padded<J, 1>(w, x1, h1, h2, q1);
-            bwd_padded<J, 1>(w, x1, h1, h2, [&](int, int o) { return o == jt ? gq : 0.f; }, g);
-        }
-        {
-            float x1[1][F], h1[1][H], h2[1][H], q1[1][J];
-#pragma unroll
-            for (int f = 0; f < F; ++f) { x1[0][f] = x[1][f]; asm volatile("" : "+f"(x1[0][f])); }
-            fwd_padded<J, 1>(w, x1, h1, h2, q1);
-            bwd_padded<J, 1>(w, x1, h1, h2, [&](int, int o) { return o == nja ? gqn : 0.f; }, g);
-        }
+        bwd_padded<J, 1>(w, x, h1, h2, [&](int, int o) { return o == carry_idx ? carry_val : 0.f; }, g);
     }
     block_reduce_store<P + 1>(g, red, partials + ((int64_t)n * gridDim.x + blockIdx.x) * (P + 1));
 }
@@ -365,61 +380,69 @@ __global__ void __launch_bounds__(kGradThreads) actor_grad_kernel(ia2c_episode_d
     if (blockIdx.x == 0 && threadIdx.x == 0 && !(d.flags & IA2C_FLAG_SKIP_ADAM)) d.actor_step[n] += 1;
     __syncthreads();
     const int64_t E = d.E, rows = (int64_t)d.T * E;
+    const ChunkPlan cp = chunk_plan(d.T, E, N);
+    const int64_t items = E * cp.n_chunks;
     const float inv_b = 1.f / (float)((int64_t)d.T * d.E_total);
     float g[P + 1];
 #pragma unroll
     for (int i = 0; i <= P; ++i) g[i] = 0.f;
-    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x) {
-        float x[2][F];
-        load_obs(d.obs + r * F, x[0]);
-        load_obs(d.obs + (r + E) * F, x[1]);
-        const int own = d.act[r * N + n], own_n = d.act[(r + E) * N + n];
-        const int ja = joint_index(n, N, own, d.partner_pred[r * N + n]);            // ia2c.py:120-121
-        const int nja = joint_index(n, N, own_n, d.partner_pred[(r + E) * N + n]);
-        float adv;
-        {   // advantage from the UPDATED critic, no gradient (ia2c.py:116-127)
-            float h1[2][H], h2[2][H], q[2][J];
-            fwd_padded<J, 2>(wc, x, h1, h2, q);
-            float qsel = 0.f, qnsel = 0.f;
-#pragma unroll
-            for (int o = 0; o < J; ++o) {
-                qsel = (o == ja) ? q[0][o] : qsel;
-                qnsel = (o == nja) ? q[1][o] : qnsel;
-            }
-            adv = (d.reward[r] + d.gamma * qnsel) - qsel;
+    for (int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; item < items; item += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t e = item % E;
+        const int t0 = (int)(item / E) * cp.chunk_len;
+        const int t1 = min(d.T, t0 + cp.chunk_len);
+        float x[1][F], q[1][J];
+        load_obs(d.obs + ((int64_t)t0 * E + e) * F, x[0]);
+        {
+            float h1[1][H], h2[1][H];
+            fwd_padded<J, 1>(wc, x, h1, h2, q);
         }
-        if (d.adv_dump) d.adv_dump[(int64_t)n * rows + r] = adv;
-        float x1[1][F], h1[1][H], h2[1][H], pp[1][A];
-#pragma unroll
-        for (int f = 0; f < F; ++f) x1[0][f] = x[0][f];
-        fwd_padded<A, 1>(w, x1, h1, h2, pp);
-        float (&p)[A] = pp[0];
-        softmax_inplace<A>(p);
-        // Categorical(probs=p): q = p/sum(p); logit = log(clamp(q)); loss_row = adv*(-logit[a]) - beta*H
-        float s = 0.f;
-#pragma unroll
-        for (int o = 0; o < A; ++o) s += p[o];
-        float ent = 0.f, qg = 0.f, neglogp = 0.f, gq[A], qq[A];
-#pragma unroll
-        for (int o = 0; o < A; ++o) {
-            const float q = p[o] / s;
-            const bool inside = (q >= kEpsClamp) && (q <= 1.f - kEpsClamp);
-            const float logit = logf(fminf(fmaxf(q, kEpsClamp), 1.f - kEpsClamp));
-            ent -= logit * q;
-            float go = d.beta * (logit + (inside ? 1.f : 0.f));
-            if (o == own) {
-                neglogp = -logit;
-                if (inside) go -= adv / q;
+        for (int t = t0; t < t1; ++t) {
+            const int64_t r = (int64_t)t * E + e;
+            float xn[1][F], qn[1][J];
+            load_obs(d.obs + (r + E) * F, xn[0]);
+            {
+                float h1[1][H], h2[1][H];
+                fwd_padded<J, 1>(wc, xn, h1, h2, qn);               // UPDATED critic, no gradient (ia2c.py:116-127)
             }
-            gq[o] = go;
-            qq[o] = q;
-            qg = fmaf(q, go, qg);
-        }
-        g[P] += adv * neglogp - d.beta * ent;
-        float dy[A];
+            const int own = d.act[r * N + n], own_n = d.act[(r + E) * N + n];
+            const int ja = joint_index(n, N, own, d.partner_pred[r * N + n]);            // ia2c.py:120-121
+            const int nja = joint_index(n, N, own_n, d.partner_pred[(r + E) * N + n]);
+            const float adv = (d.reward[r] + d.gamma * select_q<J>(qn, nja)) - select_q<J>(q, ja);
+            if (d.adv_dump) d.adv_dump[(int64_t)n * rows + r] = adv;
+            float h1[1][H], h2[1][H], pp[1][A];
+            fwd_padded<A, 1>(w, x, h1, h2, pp);
+            float (&p)[A] = pp[0];
+            softmax_inplace<A>(p);
+            // Categorical(probs=p): q = p/sum(p); logit = log(clamp(q)); loss_row = adv*(-logit[a]) - beta*H
+            float s = 0.f;
 #pragma unroll
-        for (int o = 0; o < A; ++o) dy[o] = qq[o] * (gq[o] - qg) * inv_b;   // through normalise + softmax
-        bwd_padded<A, 1>(w, x1, h1, h2, [&](int, int o) { return dy[o]; }, g);
+            for (int o = 0; o < A; ++o) s += p[o];
+            float ent = 0.f, qg = 0.f, neglogp = 0.f, gq[A], qq[A];
+#pragma unroll
+            for (int o = 0; o < A; ++o) {
+                const float qv = p[o] / s;
+                const bool inside = (qv >= kEpsClamp) && (qv <= 1.f - kEpsClamp);
+                const float logit = logf(fminf(fmaxf(qv, kEpsClamp), 1.f - kEpsClamp));
+                ent -= logit * qv;
+                float go = d.beta * (logit + (inside ? 1.f : 0.f));
+                if (o == own) {
+                    neglogp = -logit;
+                    if (inside) go -= adv / qv;
+                }
+                gq[o] = go;
+                qq[o] = qv;
+                qg = fmaf(qv, go, qg);
+            }
+            g[P] += adv * neglogp - d.beta * ent;
+            float dy[A];
+#pragma unroll
+            for (int o = 0; o < A; ++o) dy[o] = qq[o] * (gq[o] - qg) * inv_b;   // through normalise + softmax
+            bwd_padded<A, 1>(w, x, h1, h2, [&](int, int o) { return dy[o]; }, g);
+#pragma unroll
+            for (int k = 0; k < F; ++k) x[0][k] = xn[0][k];
+#pragma unroll
+            for (int o = 0; o < J; ++o) q[0][o] = qn[0][o];
+        }
     }
     block_reduce_store<P + 1>(g, red, partials + ((int64_t)n * gridDim.x + blockIdx.x) * (P + 1));
 }
@@ -493,12 +516,13 @@ __global__ void bump_steps_kernel(int32_t* step, int n) {
 }
 
 // Blocks per agent for the gradient kernels: one resident wave (2 blocks of 128 threads per SM at 255
-// registers) shared by the N agents, grid-stride over the rows, but never fewer than ~4 rows per thread.
+// registers) shared by the N agents, grid-stride over the (env, time chunk) items.
 int grad_blocks(const ia2c_episode_desc* d) {
-    const int64_t rows = (int64_t)d->T * d->E;
-    const int64_t by_rows = (rows + kGradThreads * 4 - 1) / (kGradThreads * 4);
+    const ChunkPlan cp = chunk_plan(d->T, d->E, d->N);
+    const int64_t items = d->E * cp.n_chunks;
+    const int64_t by_items = (items + kGradThreads - 1) / kGradThreads;
     const int64_t by_wave = std::max<int64_t>(1, (int64_t)kSMs * 2 / std::max(1, d->N));
-    return (int)std::max<int64_t>(1, std::min(by_rows, by_wave));
+    return (int)std::max<int64_t>(1, std::min(by_items, by_wave));
 }
 
 int validate(const ia2c_episode_desc* d, const char* who) {
@@ -648,6 +672,71 @@ extern "C" int ia2c_train_episode_host(const ia2c_episode_desc* d, const float* 
         return check_launch("memcpy D2H loss");
     if (host_ep_return && cudaMemcpyAsync(host_ep_return, d->ep_return, (size_t)d->E * sizeof(double), cudaMemcpyDeviceToHost, s) != cudaSuccess)
         return check_launch("memcpy D2H ep_return");
+    if (cudaStreamSynchronize(s) != cudaSuccess) return check_launch("stream sync");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Pipelined host-buffer entry point: n_episodes episodes whose injected uniforms live in (pinned) HOST
+// memory.  The H2D copy of episode k+1 runs on an internal copy stream while episode k computes; every
+// episode's losses and returns are read back to its own host slot; one host sync at the end.
+namespace {
+struct HostPipe {
+    cudaStream_t copy = nullptr;
+    cudaEvent_t copied[2] = {nullptr, nullptr}, consumed[2] = {nullptr, nullptr};
+    int device = -1;
+};
+thread_local HostPipe g_pipe;
+
+int pipe_init() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return check_launch("cudaGetDevice");
+    if (g_pipe.copy && g_pipe.device == dev) return 0;
+    g_pipe.device = dev;
+    if (cudaStreamCreateWithFlags(&g_pipe.copy, cudaStreamNonBlocking) != cudaSuccess) return check_launch("cudaStreamCreate");
+    for (int i = 0; i < 2; ++i) {
+        if (cudaEventCreateWithFlags(&g_pipe.copied[i], cudaEventDisableTiming) != cudaSuccess) return check_launch("cudaEventCreate");
+        if (cudaEventCreateWithFlags(&g_pipe.consumed[i], cudaEventDisableTiming) != cudaSuccess) return check_launch("cudaEventCreate");
+    }
+    return 0;
+}
+}  // namespace
+
+extern "C" int ia2c_train_episodes_host(const ia2c_episode_desc* d, float* stage_b_u_action, double* stage_b_u_belief,
+                                        int32_t n_episodes, const float* const* host_u_action,
+                                        const double* const* host_u_belief, float* host_loss_out,
+                                        double* host_ep_return, void* stream) {
+    if (int rc = validate(d, "ia2c_train_episodes_host")) return rc;
+    IA2C_REQUIRE(!(d->flags & IA2C_FLAG_SKIP_ADAM), "ia2c_train_episodes_host: single-rank entry point (SKIP_ADAM set)");
+    IA2C_REQUIRE(n_episodes > 0 && host_u_action && host_u_belief && host_loss_out && host_ep_return, "ia2c_train_episodes_host: null host pointer or n_episodes=%d", n_episodes);
+    IA2C_REQUIRE(d->inj_u_action && d->inj_u_belief && stage_b_u_action && stage_b_u_belief, "ia2c_train_episodes_host: two device staging sets are required");
+    if (int rc = pipe_init()) return rc;
+    cudaStream_t s = as_stream(stream);
+    const size_t n_act = (size_t)(d->T + 1) * d->E * d->N;
+    const size_t b_act = n_act * sizeof(float), b_bel = n_act * (d->N - 1) * sizeof(double);
+    float* st_a[2] = {const_cast<float*>(d->inj_u_action), stage_b_u_action};
+    double* st_b[2] = {const_cast<double*>(d->inj_u_belief), stage_b_u_belief};
+    // the copy stream must not overwrite a staging set that earlier work on `s` may still read
+    if (cudaEventRecord(g_pipe.consumed[0], s) != cudaSuccess || cudaEventRecord(g_pipe.consumed[1], s) != cudaSuccess)
+        return check_launch("cudaEventRecord");
+    ia2c_episode_desc e = *d;
+    for (int k = 0; k < n_episodes; ++k) {
+        const int b = k & 1;
+        cudaStreamWaitEvent(g_pipe.copy, g_pipe.consumed[b], 0);
+        if (cudaMemcpyAsync(st_a[b], host_u_action[k], b_act, cudaMemcpyHostToDevice, g_pipe.copy) != cudaSuccess ||
+            cudaMemcpyAsync(st_b[b], host_u_belief[k], b_bel, cudaMemcpyHostToDevice, g_pipe.copy) != cudaSuccess)
+            return check_launch("memcpy H2D uniforms");
+        cudaEventRecord(g_pipe.copied[b], g_pipe.copy);
+        cudaStreamWaitEvent(s, g_pipe.copied[b], 0);
+        e.inj_u_action = st_a[b];
+        e.inj_u_belief = st_b[b];
+        e.episode = d->episode + (uint32_t)k;
+        if (int rc = ia2c_train_episode(&e, stream)) return rc;
+        cudaEventRecord(g_pipe.consumed[b], s);
+        if (cudaMemcpyAsync(host_loss_out + (size_t)k * 2 * d->N, d->loss_out, 2 * (size_t)d->N * sizeof(float), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+            cudaMemcpyAsync(host_ep_return + (size_t)k * d->E, d->ep_return, (size_t)d->E * sizeof(double), cudaMemcpyDeviceToHost, s) != cudaSuccess)
+            return check_launch("memcpy D2H results");
+    }
     if (cudaStreamSynchronize(s) != cudaSuccess) return check_launch("stream sync");
     return 0;
 }

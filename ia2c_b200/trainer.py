@@ -190,6 +190,79 @@ class IA2CTrainer:
         self.episode += 1
         return self._record_stats()
 
+    def train_episodes_host(self, host_u_action, host_u_belief):
+        """Pipelined end-to-end form: lists of per-episode pinned host tapes in, per-episode losses and returns
+        out.  The H2D copy of episode k+1 overlaps episode k (``ia2c_train_episodes_host``); single rank."""
+        n = len(host_u_action)
+        T, E, N, K = self.T, self.E, self.N, self.K
+        if self.world > 1:
+            return self._train_episodes_host_multirank(host_u_action, host_u_belief)
+        if self.inj_u_action is None or self.inj_u_belief is None:
+            self.inject(u_action=torch.zeros(T + 1, E, N), u_belief=torch.zeros(T + 1, E, N, K, dtype=torch.float64))
+        if getattr(self, "_stage_b", None) is None:
+            self._stage_b = (torch.empty_like(self.inj_u_action), torch.empty_like(self.inj_u_belief))
+        if getattr(self, "_h_multi", None) is None or self._h_multi[0].shape[0] < n:
+            self._h_multi = (torch.zeros(n, 2, N, dtype=torch.float32).pin_memory(),
+                             torch.zeros(n, E, dtype=torch.float64).pin_memory())
+        pa = (C.c_void_p * n)(*[t.data_ptr() for t in host_u_action])
+        pb = (C.c_void_p * n)(*[t.data_ptr() for t in host_u_belief])
+        self.desc.episode = self.episode
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.ia2c_train_episodes_host(
+                C.byref(self.desc), self._stage_b[0].data_ptr(), self._stage_b[1].data_ptr(), n, pa, pb,
+                self._h_multi[0].data_ptr(), self._h_multi[1].data_ptr(), self._stream()), "ia2c_train_episodes_host")
+        self.episode += n
+        out = []
+        for k in range(n):
+            self._h_loss.copy_(self._h_multi[0][k])
+            self._h_return.copy_(self._h_multi[1][k])
+            out.append(self._record_stats())
+        return out
+
+    def _train_episodes_host_multirank(self, host_u_action, host_u_belief):
+        """Same pipeline with torch streams/events around the per-phase entry points (the NCCL all-reduces sit
+        between them, so the single C call cannot be used)."""
+        n = len(host_u_action)
+        T, E, N, K = self.T, self.E, self.N, self.K
+        if self.inj_u_action is None or self.inj_u_belief is None:
+            self.inject(u_action=torch.zeros(T + 1, E, N), u_belief=torch.zeros(T + 1, E, N, K, dtype=torch.float64))
+        if getattr(self, "_stage_b", None) is None:
+            self._stage_b = (torch.empty_like(self.inj_u_action), torch.empty_like(self.inj_u_belief))
+        if getattr(self, "_h_multi", None) is None or self._h_multi[0].shape[0] < n:
+            self._h_multi = (torch.zeros(n, 2, N, dtype=torch.float32).pin_memory(),
+                             torch.zeros(n, E, dtype=torch.float64).pin_memory())
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        stage = [(self.inj_u_action, self.inj_u_belief), self._stage_b]
+        cur = torch.cuda.current_stream(self.device)
+        copied = [torch.cuda.Event(), torch.cuda.Event()]
+        consumed = [torch.cuda.Event(), torch.cuda.Event()]
+        for ev_ in consumed:
+            ev_.record(cur)
+        for k in range(n):
+            b = k & 1
+            with torch.cuda.stream(self._copy_stream):
+                self._copy_stream.wait_event(consumed[b])
+                stage[b][0].copy_(host_u_action[k], non_blocking=True)
+                stage[b][1].copy_(host_u_belief[k], non_blocking=True)
+                copied[b].record(self._copy_stream)
+            cur.wait_event(copied[b])
+            self.desc.inj_u_action, self.desc.inj_u_belief = stage[b][0].data_ptr(), stage[b][1].data_ptr()
+            self.rollout()
+            self.update()
+            consumed[b].record(cur)
+            self.episode += 1
+            self._h_multi[0][k].copy_(self.loss_out, non_blocking=True)
+            self._h_multi[1][k].copy_(self.ep_return, non_blocking=True)
+        cur.synchronize()
+        self.desc.inj_u_action, self.desc.inj_u_belief = self.inj_u_action.data_ptr(), self.inj_u_belief.data_ptr()
+        out = []
+        for k in range(n):
+            self._h_loss.copy_(self._h_multi[0][k])
+            self._h_return.copy_(self._h_multi[1][k])
+            out.append(self._record_stats())
+        return out
+
     def read_stats(self):
         self._h_loss.copy_(self.loss_out, non_blocking=True)
         self._h_return.copy_(self.ep_return, non_blocking=True)

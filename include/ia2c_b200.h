@@ -230,6 +230,16 @@ int ia2c_train_episode_host(const ia2c_episode_desc* d, const float* host_u_acti
                             const double* host_u_belief, float* host_loss_out, double* host_ep_return,
                             void* stream);
 
+/* Pipelined form of the above for n_episodes consecutive episodes: host_u_action[k] / host_u_belief[k] are
+ * the (pinned) host tapes of episode k; the H2D copy of episode k+1 overlaps the compute of episode k on an
+ * internal copy stream (two device staging sets: desc.inj_u_* and stage_b_*); every episode's losses
+ * (host_loss_out float[n,2,N]) and returns (host_ep_return double[n,E]) are read back; one sync at the end.
+ * Episode numbers are desc.episode .. desc.episode + n_episodes - 1. */
+int ia2c_train_episodes_host(const ia2c_episode_desc* d, float* stage_b_u_action, double* stage_b_u_belief,
+                             int32_t n_episodes, const float* const* host_u_action,
+                             const double* const* host_u_belief, float* host_loss_out, double* host_ep_return,
+                             void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -168,3 +168,20 @@ def test_fused_rollout_rejects_unsupported_shapes():
     tr = make_trainer(4, 9, 5, _random_init(9, 5, seed=1), fused_rollout=True)
     with pytest.raises(_lib.IA2CError, match="FUSED_ROLLOUT"):
         tr.train_episode()
+
+
+def test_pipelined_host_episodes_match_sequential_calls():
+    import torch
+    E, N, M, T, n = 40, 2, 5, 30, 5
+    init = _random_init(N, M, seed=9)
+    rng = np.random.RandomState(1)
+    ua = [torch.from_numpy(rng.rand(T + 1, E, N).astype(np.float32)).pin_memory() for _ in range(n)]
+    ub = [torch.from_numpy(rng.rand(T + 1, E, N, N - 1)).pin_memory() for _ in range(n)]
+    a = make_trainer(E, N, M, init, fused_rollout=True)
+    b = make_trainer(E, N, M, init, fused_rollout=True)
+    piped = a.train_episodes_host(ua, ub)
+    seq = [b.train_episode_host(x, y) for x, y in zip(ua, ub)]
+    for p, q in zip(piped, seq):
+        assert np.array_equal(p["ep_return"], q["ep_return"]) and np.array_equal(p["critic_loss"], q["critic_loss"])
+        assert np.array_equal(p["actor_loss"], q["actor_loss"])
+    assert np.array_equal(host(a.actor_params), host(b.actor_params)) and a.episode == b.episode == n
