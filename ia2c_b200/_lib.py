@@ -73,6 +73,7 @@ SIGNATURES = {
     "ia2c_apply_adam": (C.c_int, [_DP, i32, vp]),
     "ia2c_train_episode": (C.c_int, [_DP, vp]),
     "ia2c_train_episode_host": (C.c_int, [_DP, vp, vp, vp, vp, vp]),
+    "ia2c_train_episode_timed": (C.c_int, [_DP, vp, vp]),
     "ia2c_train_episodes_host": (C.c_int, [_DP, vp, vp, i32, C.POINTER(vp), C.POINTER(vp), vp, vp, vp]),
 }
 

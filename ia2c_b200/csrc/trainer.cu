@@ -21,6 +21,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "mlp_f2.cuh"
 
 namespace ia2c {
 int rollout_fused_supported(int N, int M);                                  // rollout_fused.cu
@@ -157,138 +158,7 @@ __device__ __forceinline__ void load_obs(const float* __restrict__ p, float (&x)
     x[0] = a.x; x[1] = a.y; x[2] = b.x; x[3] = b.y; x[4] = c.x; x[5] = c.y;
 }
 
-// ---- shared-memory weights for the gradient kernels -----------------------------------------------
-// At hidden_size 6 every FFMA needs one weight, and a 32-bit broadcast LDS per FFMA makes the kernels
-// LSU-bound (one shared-memory wavefront per cycle per SM; measured, profiles/).  The weights are
-// therefore staged in a PADDED layout — every 6-wide row padded to 8 floats — so a row is fetched by
-// two 128-bit broadcast loads, and each fetched row is used for NX inputs at once (obs and next_obs).
-template <int O>
-struct PadLayout {
-    static constexpr int w1 = 0, b1 = 48, w2 = 56, b2 = 104, w3 = 112, b3 = 112 + O * 8, size = b3 + ((O + 3) / 4) * 4;
-};
-
-template <int O>
-__device__ __forceinline__ void stage_padded(float* sw, const float* __restrict__ flat) {
-    using L = PadLayout<O>;
-    using D = MlpDims<F, O>;
-    for (int i = threadIdx.x; i < L::size; i += blockDim.x) {
-        float v = 0.f;
-        const int r = (i - 0) / 8, c = i % 8;
-        if (i < L::b1) { if (c < F) v = flat[D::w1 + r * F + c]; }
-        else if (i < L::w2) { if (i - L::b1 < H) v = flat[D::b1 + i - L::b1]; }
-        else if (i < L::b2) { const int rr = (i - L::w2) / 8; if (c < H) v = flat[D::w2 + rr * H + c]; }
-        else if (i < L::w3) { if (i - L::b2 < H) v = flat[D::b2 + i - L::b2]; }
-        else if (i < L::b3) { const int rr = (i - L::w3) / 8; if (c < H) v = flat[D::w3 + rr * H + c]; }
-        else { if (i - L::b3 < O) v = flat[D::b3 + i - L::b3]; }
-        sw[i] = v;
-    }
-}
-
-__device__ __forceinline__ void row8(const float* p, float (&r)[8]) {
-    const float4 a = *reinterpret_cast<const float4*>(p);
-    const float4 b = *reinterpret_cast<const float4*>(p + 4);
-    r[0] = a.x; r[1] = a.y; r[2] = a.z; r[3] = a.w; r[4] = b.x; r[5] = b.y; r[6] = b.z; r[7] = b.w;
-}
-
-// Forward of NX inputs through one network; each weight row is fetched once for all NX inputs.
-template <int O, int NX>
-__device__ __forceinline__ void fwd_padded(const float* sw, const float (&x)[NX][F], float (&h1)[NX][H],
-                                           float (&h2)[NX][H], float (&y)[NX][O]) {
-    using L = PadLayout<O>;
-    float r[8], bias[8];
-    row8(sw + L::b1, bias);
-#pragma unroll
-    for (int j = 0; j < H; ++j) {
-        row8(sw + L::w1 + j * 8, r);
-#pragma unroll
-        for (int n = 0; n < NX; ++n) {
-            float acc = bias[j];
-#pragma unroll
-            for (int f = 0; f < F; ++f) acc = fmaf(r[f], x[n][f], acc);
-            h1[n][j] = fmaxf(acc, 0.f);
-        }
-    }
-    row8(sw + L::b2, bias);
-#pragma unroll
-    for (int j = 0; j < H; ++j) {
-        row8(sw + L::w2 + j * 8, r);
-#pragma unroll
-        for (int n = 0; n < NX; ++n) {
-            float acc = bias[j];
-#pragma unroll
-            for (int k = 0; k < H; ++k) acc = fmaf(r[k], h1[n][k], acc);
-            h2[n][j] = fmaxf(acc, 0.f);
-        }
-    }
-#pragma unroll
-    for (int o = 0; o < O; ++o) {
-        row8(sw + L::w3 + o * 8, r);
-        const float bo = sw[L::b3 + o];
-#pragma unroll
-        for (int n = 0; n < NX; ++n) {
-            float acc = bo;
-#pragma unroll
-            for (int k = 0; k < H; ++k) acc = fmaf(r[k], h2[n][k], acc);
-            y[n][o] = acc;
-        }
-    }
-}
-
-// Backward of NX inputs (dy wrt the pre-softmax outputs), accumulating into g (flat MlpDims layout).
-// dy(n, o) is a callable so that sparse output gradients (the critic's single selected Q) need no array.
-template <int O, int NX, int GN, typename DY>
-__device__ __forceinline__ void bwd_padded(const float* sw, const float (&x)[NX][F], const float (&h1)[NX][H],
-                                           const float (&h2)[NX][H], DY dy, float (&g)[GN]) {
-    using L = PadLayout<O>;
-    using D = MlpDims<F, O>;
-    static_assert(GN >= D::P, "gradient accumulator too small");
-    float r[8];
-    float dh2[NX][H], dh1[NX][H];
-#pragma unroll
-    for (int n = 0; n < NX; ++n)
-#pragma unroll
-        for (int k = 0; k < H; ++k) dh2[n][k] = dh1[n][k] = 0.f;
-#pragma unroll
-    for (int o = 0; o < O; ++o) {
-        row8(sw + L::w3 + o * 8, r);
-#pragma unroll
-        for (int n = 0; n < NX; ++n) {
-            const float dyv = dy(n, o);
-            g[D::b3 + o] += dyv;
-#pragma unroll
-            for (int k = 0; k < H; ++k) {
-                g[D::w3 + o * H + k] = fmaf(dyv, h2[n][k], g[D::w3 + o * H + k]);
-                dh2[n][k] = fmaf(dyv, r[k], dh2[n][k]);
-            }
-        }
-    }
-#pragma unroll
-    for (int j = 0; j < H; ++j) {
-        row8(sw + L::w2 + j * 8, r);
-#pragma unroll
-        for (int n = 0; n < NX; ++n) {
-            const float dz = h2[n][j] > 0.f ? dh2[n][j] : 0.f;
-            g[D::b2 + j] += dz;
-#pragma unroll
-            for (int k = 0; k < H; ++k) {
-                g[D::w2 + j * H + k] = fmaf(dz, h1[n][k], g[D::w2 + j * H + k]);
-                dh1[n][k] = fmaf(dz, r[k], dh1[n][k]);
-            }
-        }
-    }
-#pragma unroll
-    for (int j = 0; j < H; ++j) {
-#pragma unroll
-        for (int n = 0; n < NX; ++n) {
-            const float dz = h1[n][j] > 0.f ? dh1[n][j] : 0.f;
-            g[D::b1 + j] += dz;
-#pragma unroll
-            for (int f = 0; f < F; ++f) g[D::w1 + j * F + f] = fmaf(dz, x[n][f], g[D::w1 + j * F + f]);
-        }
-    }
-}
-
-// ---- gradient kernels: one thread per (agent, env, time chunk) ---------------------------------------
+// ---- gradient kernels: one thread per (agent, env, time chunk), packed fp32 math (mlp_f2.cuh) ----------
 // next_obs[t] IS obs[t+1] (trajectory layout), so a thread that walks a chunk [t0,t1) of one env's
 // time axis evaluates the critic ONCE per observation (L+1 forwards for L rows instead of 2L) and, in the
 // critic phase, back-propagates ONCE per observation with the two output-gradient contributions it
@@ -307,111 +177,115 @@ __host__ __device__ inline ChunkPlan chunk_plan(int T, int64_t E, int N) {
     return p;
 }
 
-template <int O>
-__device__ __forceinline__ float select_q(const float (&q)[1][O], int idx) {
-    float v = 0.f;
+template <int GN>
+__device__ __forceinline__ void unpack_g2(const float2 (&g2)[GN], float (&g)[2 * GN]) {
 #pragma unroll
-    for (int o = 0; o < O; ++o) v = (o == idx) ? q[0][o] : v;
-    return v;
+    for (int i = 0; i < GN; ++i) { g[2 * i] = g2[i].x; g[2 * i + 1] = g2[i].y; }
 }
 
 // partial row layout: P gradient entries then the loss partial.
 __global__ void __launch_bounds__(kGradThreads) critic_grad_kernel(ia2c_episode_desc d, float* __restrict__ partials) {
-    constexpr int P = kCriticP;
-    __shared__ __align__(16) float w[PadLayout<J>::size];
+    constexpr int P = kCriticP, GN = F2<J>::G2;   // 148 floats = 74 float2
+    __shared__ __align__(16) float w[SmemNet<J>::size];
     __shared__ float red[(kGradThreads / 32) * (P + 1)];
     const int n = blockIdx.y, N = d.N;
-    stage_padded<J>(w, d.critic_params + (int64_t)n * P);
+    stage_smemnet<J>(w, d.critic_params + (int64_t)n * P);
     if (blockIdx.x == 0 && threadIdx.x == 0 && !(d.flags & IA2C_FLAG_SKIP_ADAM)) d.critic_step[n] += 1;
     __syncthreads();
     const int64_t E = d.E, rows = (int64_t)d.T * E;
     const ChunkPlan cp = chunk_plan(d.T, E, N);
     const int64_t items = E * cp.n_chunks;
     const float inv_b = 1.f / (float)((int64_t)d.T * d.E_total);
-    float g[P + 1];
+    float2 g2[GN];
 #pragma unroll
-    for (int i = 0; i <= P; ++i) g[i] = 0.f;
+    for (int i = 0; i < GN; ++i) g2[i] = make_float2(0.f, 0.f);
+    float loss = 0.f;
     for (int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; item < items; item += (int64_t)gridDim.x * blockDim.x) {
         const int64_t e = item % E;
         const int t0 = (int)(item / E) * cp.chunk_len;
         const int t1 = min(d.T, t0 + cp.chunk_len);
-        float x[1][F], h1[1][H], h2[1][H], q[1][J];
-        load_obs(d.obs + ((int64_t)t0 * E + e) * F, x[0]);
-        fwd_padded<J, 1>(w, x, h1, h2, q);
+        float x[kIn], q[J];
+        float2 h1[3], h2[3];
+        load_obs6(d.obs + ((int64_t)t0 * E + e) * kIn, x);
+        fwd_f2<J>(w, x, h1, h2, q);
         int carry_idx = -1;          // pending bootstrap gradient for the CURRENT observation (from row t-1)
         float carry_val = 0.f;
         for (int t = t0; t < t1; ++t) {
             const int64_t r = (int64_t)t * E + e;
-            float xn[1][F], h1n[1][H], h2n[1][H], qn[1][J];
-            load_obs(d.obs + (r + E) * F, xn[0]);                    // next_obs[t] = obs[t+1]
-            fwd_padded<J, 1>(w, xn, h1n, h2n, qn);
+            float xn[kIn], qn[J];
+            float2 h1n[3], h2n[3];
+            load_obs6(d.obs + (r + E) * kIn, xn);                    // next_obs[t] = obs[t+1]
+            fwd_f2<J>(w, xn, h1n, h2n, qn);
             const int own = d.act[r * N + n], own_n = d.act[(r + E) * N + n];
             const int jt = joint_index(n, N, own, d.partner_true[r * N + n]);            // ia2c.py:112
             const int nja = joint_index(n, N, own_n, d.partner_pred[(r + E) * N + n]);   // ia2c.py:104-105
-            const float target = d.reward[r] + d.gamma * select_q<J>(qn, nja);           // ia2c.py:110 (Q8)
-            const float delta = target - select_q<J>(q, jt);
+            const float target = d.reward[r] + d.gamma * select_out<J>(qn, nja);         // ia2c.py:110 (Q8)
+            const float delta = target - select_out<J>(q, jt);
             if (d.target_dump) d.target_dump[(int64_t)n * rows + r] = target;
-            g[P] = fmaf(delta, delta, g[P]);
+            loss = fmaf(delta, delta, loss);
             const float gq = -2.f * delta * inv_b;                   // dL/dQ(obs_t)[jt]
-            bwd_padded<J, 1>(w, x, h1, h2,
-                             [&](int, int o) { return (o == jt ? gq : 0.f) + (o == carry_idx ? carry_val : 0.f); }, g);
+            bwd_f2<J>(w, x, h1, h2, [&](int o) { return (o == jt ? gq : 0.f) + (o == carry_idx ? carry_val : 0.f); }, g2);
             carry_idx = nja;
             carry_val = 2.f * d.gamma * delta * inv_b;               // dL/dQ(next_obs_t)[nja]: residual gradient
 #pragma unroll
-            for (int k = 0; k < F; ++k) x[0][k] = xn[0][k];
+            for (int k = 0; k < kIn; ++k) x[k] = xn[k];
 #pragma unroll
-            for (int k = 0; k < H; ++k) { h1[0][k] = h1n[0][k]; h2[0][k] = h2n[0][k]; }
+            for (int k = 0; k < 3; ++k) { h1[k] = h1n[k]; h2[k] = h2n[k]; }
 #pragma unroll
-            for (int o = 0; o < J; ++o) q[0][o] = qn[0][o];
+            for (int o = 0; o < J; ++o) q[o] = qn[o];
         }
-        bwd_padded<J, 1>(w, x, h1, h2, [&](int, int o) { return o == carry_idx ? carry_val : 0.f; }, g);
+        bwd_f2<J>(w, x, h1, h2, [&](int o) { return o == carry_idx ? carry_val : 0.f; }, g2);
     }
-    block_reduce_store<P + 1>(g, red, partials + ((int64_t)n * gridDim.x + blockIdx.x) * (P + 1));
+    float g[2 * GN];
+    unpack_g2(g2, g);
+    g[P] = loss;
+    block_reduce_store<P + 1>(reinterpret_cast<float(&)[P + 1]>(g), red, partials + ((int64_t)n * gridDim.x + blockIdx.x) * (P + 1));
 }
 
 __global__ void __launch_bounds__(kGradThreads) actor_grad_kernel(ia2c_episode_desc d, float* __restrict__ partials) {
-    constexpr int P = kActorP, PC = kCriticP;
-    __shared__ __align__(16) float wc[PadLayout<J>::size];
-    __shared__ __align__(16) float w[PadLayout<A>::size];
+    constexpr int P = kActorP, PC = kCriticP, GN = F2<A>::G2;   // 106 floats = 53 float2
+    __shared__ __align__(16) float wc[SmemNet<J>::size];
+    __shared__ __align__(16) float w[SmemNet<A>::size];
     __shared__ float red[(kGradThreads / 32) * (P + 1)];
     const int n = blockIdx.y, N = d.N;
-    stage_padded<J>(wc, d.critic_params + (int64_t)n * PC);
-    stage_padded<A>(w, d.actor_params + (int64_t)n * P);
+    stage_smemnet<J>(wc, d.critic_params + (int64_t)n * PC);
+    stage_smemnet<A>(w, d.actor_params + (int64_t)n * P);
     if (blockIdx.x == 0 && threadIdx.x == 0 && !(d.flags & IA2C_FLAG_SKIP_ADAM)) d.actor_step[n] += 1;
     __syncthreads();
     const int64_t E = d.E, rows = (int64_t)d.T * E;
     const ChunkPlan cp = chunk_plan(d.T, E, N);
     const int64_t items = E * cp.n_chunks;
     const float inv_b = 1.f / (float)((int64_t)d.T * d.E_total);
-    float g[P + 1];
+    float2 g2[GN];
 #pragma unroll
-    for (int i = 0; i <= P; ++i) g[i] = 0.f;
+    for (int i = 0; i < GN; ++i) g2[i] = make_float2(0.f, 0.f);
+    float loss = 0.f;
     for (int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; item < items; item += (int64_t)gridDim.x * blockDim.x) {
         const int64_t e = item % E;
         const int t0 = (int)(item / E) * cp.chunk_len;
         const int t1 = min(d.T, t0 + cp.chunk_len);
-        float x[1][F], q[1][J];
-        load_obs(d.obs + ((int64_t)t0 * E + e) * F, x[0]);
+        float x[kIn], q[J];
+        load_obs6(d.obs + ((int64_t)t0 * E + e) * kIn, x);
         {
-            float h1[1][H], h2[1][H];
-            fwd_padded<J, 1>(wc, x, h1, h2, q);
+            float2 h1[3], h2[3];
+            fwd_f2<J>(wc, x, h1, h2, q);
         }
         for (int t = t0; t < t1; ++t) {
             const int64_t r = (int64_t)t * E + e;
-            float xn[1][F], qn[1][J];
-            load_obs(d.obs + (r + E) * F, xn[0]);
+            float xn[kIn], qn[J];
+            load_obs6(d.obs + (r + E) * kIn, xn);
             {
-                float h1[1][H], h2[1][H];
-                fwd_padded<J, 1>(wc, xn, h1, h2, qn);               // UPDATED critic, no gradient (ia2c.py:116-127)
+                float2 h1[3], h2[3];
+                fwd_f2<J>(wc, xn, h1, h2, qn);                       // UPDATED critic, no gradient (ia2c.py:116-127)
             }
             const int own = d.act[r * N + n], own_n = d.act[(r + E) * N + n];
             const int ja = joint_index(n, N, own, d.partner_pred[r * N + n]);            // ia2c.py:120-121
             const int nja = joint_index(n, N, own_n, d.partner_pred[(r + E) * N + n]);
-            const float adv = (d.reward[r] + d.gamma * select_q<J>(qn, nja)) - select_q<J>(q, ja);
+            const float adv = (d.reward[r] + d.gamma * select_out<J>(qn, nja)) - select_out<J>(q, ja);
             if (d.adv_dump) d.adv_dump[(int64_t)n * rows + r] = adv;
-            float h1[1][H], h2[1][H], pp[1][A];
-            fwd_padded<A, 1>(w, x, h1, h2, pp);
-            float (&p)[A] = pp[0];
+            float2 h1[3], h2[3];
+            float p[A];
+            fwd_f2<A>(w, x, h1, h2, p);
             softmax_inplace<A>(p);
             // Categorical(probs=p): q = p/sum(p); logit = log(clamp(q)); loss_row = adv*(-logit[a]) - beta*H
             float s = 0.f;
@@ -433,18 +307,21 @@ __global__ void __launch_bounds__(kGradThreads) actor_grad_kernel(ia2c_episode_d
                 qq[o] = qv;
                 qg = fmaf(qv, go, qg);
             }
-            g[P] += adv * neglogp - d.beta * ent;
+            loss += adv * neglogp - d.beta * ent;
             float dy[A];
 #pragma unroll
             for (int o = 0; o < A; ++o) dy[o] = qq[o] * (gq[o] - qg) * inv_b;   // through normalise + softmax
-            bwd_padded<A, 1>(w, x, h1, h2, [&](int, int o) { return dy[o]; }, g);
+            bwd_f2<A>(w, x, h1, h2, [&](int o) { return dy[o]; }, g2);
 #pragma unroll
-            for (int k = 0; k < F; ++k) x[0][k] = xn[0][k];
+            for (int k = 0; k < kIn; ++k) x[k] = xn[k];
 #pragma unroll
-            for (int o = 0; o < J; ++o) q[0][o] = qn[0][o];
+            for (int o = 0; o < J; ++o) q[o] = qn[o];
         }
     }
-    block_reduce_store<P + 1>(g, red, partials + ((int64_t)n * gridDim.x + blockIdx.x) * (P + 1));
+    float g[2 * GN];
+    unpack_g2(g2, g);
+    g[P] = loss;
+    block_reduce_store<P + 1>(reinterpret_cast<float(&)[P + 1]>(g), red, partials + ((int64_t)n * gridDim.x + blockIdx.x) * (P + 1));
 }
 
 // Sum partials over blocks (fixed order) -> grad[n][0..P] (slot P = loss); optionally Adam.
@@ -739,4 +616,35 @@ extern "C" int ia2c_train_episodes_host(const ia2c_episode_desc* d, float* stage
     }
     if (cudaStreamSynchronize(s) != cudaSuccess) return check_launch("stream sync");
     return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Profiling entry point: one episode with a CUDA event between every kernel launch group (on the launching
+// stream), synchronised at the end.  ms_out[5] = {rollout, critic gradient, critic reduce+Adam, actor gradient,
+// actor reduce+Adam} in milliseconds, warm caches — what bench.py reports as per-kernel durations.
+extern "C" int ia2c_train_episode_timed(const ia2c_episode_desc* d, float* host_ms_out, void* stream) {
+    if (int rc = validate(d, "ia2c_train_episode_timed")) return rc;
+    if (int rc = check_update_ptrs(d, "ia2c_train_episode_timed")) return rc;
+    IA2C_REQUIRE(host_ms_out != nullptr, "ia2c_train_episode_timed: null output");
+    cudaStream_t s = as_stream(stream);
+    cudaEvent_t ev[6];
+    for (auto& e : ev) if (cudaEventCreate(&e) != cudaSuccess) return check_launch("cudaEventCreate");
+    int rc = 0;
+    const int apply = !(d->flags & IA2C_FLAG_SKIP_ADAM);
+    dim3 grid(grad_blocks(d), d->N);
+    cudaEventRecord(ev[0], s);
+    rc = ia2c_rollout(d, stream);
+    cudaEventRecord(ev[1], s);
+    if (!rc) { critic_grad_kernel<<<grid, kGradThreads, 0, s>>>(*d, d->partials); rc = check_launch("critic_grad_kernel"); }
+    cudaEventRecord(ev[2], s);
+    if (!rc) rc = run_reduce(d, 0, 1, apply, s);
+    cudaEventRecord(ev[3], s);
+    if (!rc) { actor_grad_kernel<<<grid, kGradThreads, 0, s>>>(*d, d->partials); rc = check_launch("actor_grad_kernel"); }
+    cudaEventRecord(ev[4], s);
+    if (!rc) rc = run_reduce(d, 1, 1, apply, s);
+    cudaEventRecord(ev[5], s);
+    if (cudaStreamSynchronize(s) != cudaSuccess && !rc) rc = check_launch("stream sync");
+    for (int i = 0; i < 5 && !rc; ++i) cudaEventElapsedTime(&host_ms_out[i], ev[i], ev[i + 1]);
+    for (auto& e : ev) cudaEventDestroy(e);
+    return rc;
 }

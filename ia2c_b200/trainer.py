@@ -263,6 +263,18 @@ class IA2CTrainer:
             out.append(self._record_stats())
         return out
 
+    def train_episode_timed(self):
+        """One episode with CUDA events between the kernels (profiling): returns the five warm durations in ms
+        {rollout, critic_grad, critic_reduce_adam, actor_grad, actor_reduce_adam}.  Single rank."""
+        if self.world > 1:
+            raise _lib.IA2CError("train_episode_timed is the single-rank profiling entry point")
+        ms = (C.c_float * 5)()
+        self.desc.episode = self.episode
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.ia2c_train_episode_timed(C.byref(self.desc), ms, self._stream()), "ia2c_train_episode_timed")
+        self.episode += 1
+        return dict(zip(("rollout", "critic_grad", "critic_reduce_adam", "actor_grad", "actor_reduce_adam"), list(ms)))
+
     def read_stats(self):
         self._h_loss.copy_(self.loss_out, non_blocking=True)
         self._h_return.copy_(self.ep_return, non_blocking=True)

@@ -230,6 +230,11 @@ int ia2c_train_episode_host(const ia2c_episode_desc* d, const float* host_u_acti
                             const double* host_u_belief, float* host_loss_out, double* host_ep_return,
                             void* stream);
 
+/* Profiling form of ia2c_train_episode: CUDA events between the kernel launch groups on `stream`, one sync at
+ * the end.  host_ms_out float[5] = {rollout, critic gradient, critic reduce+Adam, actor gradient, actor
+ * reduce+Adam} in milliseconds. */
+int ia2c_train_episode_timed(const ia2c_episode_desc* d, float* host_ms_out, void* stream);
+
 /* Pipelined form of the above for n_episodes consecutive episodes: host_u_action[k] / host_u_belief[k] are
  * the (pinned) host tapes of episode k; the H2D copy of episode k+1 overlaps the compute of episode k on an
  * internal copy stream (two device staging sets: desc.inj_u_* and stage_b_*); every episode's losses
