@@ -16,6 +16,7 @@ i32, i64, u32, u64, f32, f64 = C.c_int32, C.c_int64, C.c_uint32, C.c_uint64, C.c
 
 FLAG_FUSED_ROLLOUT = 1
 FLAG_SKIP_ADAM = 2
+FLAG_FUSED_CRITIC = 4
 BELIEF_RECORD = 8
 ACTOR_P = 105
 CRITIC_P = 147

@@ -62,8 +62,9 @@ __device__ __forceinline__ void load_regnet(RegNet<O>& R, const float* __restric
 }
 
 template <int O>
-__device__ __forceinline__ void forward_regnet(const RegNet<O>& R, const float (&x)[kIn], float (&y)[O]) {
-    float2 h1[3], h2[3], yo[F2<O>::OP];
+__device__ __forceinline__ void forward_regnet(const RegNet<O>& R, const float (&x)[kIn], float2 (&h1)[3], float2 (&h2)[3],
+                                               float (&y)[O]) {
+    float2 yo[F2<O>::OP];
 #pragma unroll
     for (int p = 0; p < 3; ++p) h1[p] = R.b1[p];
 #pragma unroll
@@ -86,6 +87,12 @@ __device__ __forceinline__ void forward_regnet(const RegNet<O>& R, const float (
         for (int p = 0; p < F2<O>::OP; ++p) yo[p] = __ffma2_rn(R.w3[k][p], bcast((k & 1) ? h2[k / 2].y : h2[k / 2].x), yo[p]);
 #pragma unroll
     for (int o = 0; o < O; ++o) y[o] = (o & 1) ? yo[o / 2].y : yo[o / 2].x;
+}
+
+template <int O>
+__device__ __forceinline__ void forward_regnet(const RegNet<O>& R, const float (&x)[kIn], float (&y)[O]) {
+    float2 h1[3], h2[3];
+    forward_regnet<O>(R, x, h1, h2, y);
 }
 
 // ------------------------------------------------------------------ shared-memory weights (gradient kernels)
@@ -251,6 +258,80 @@ __device__ __forceinline__ void bwd_f2(const float* sw, const float (&x)[kIn], c
 #pragma unroll
         for (int q = 0; q < 3; ++q)
             g2[(D::w1 + j * kIn) / 2 + q] = __ffma2_rn(x2[q], bcast(dz), g2[(D::w1 + j * kIn) / 2 + q]);
+    }
+}
+
+// ---- register-resident backward (fused rollout, critic-backprop stage) ------------------------------------
+// Natural row pairs of W3 and W2 in registers; accumulates the W3/b3/W2/b2 gradient and hands dz1 to the stage
+// that owns the W1/b1 gradient (splitting the 147 accumulators over two warps keeps both below the register
+// limit WITH their weights resident, so neither waits on shared-memory loads).
+template <int O>
+struct RegBack {
+    float2 w3[O][3], w2[H][3];
+};
+template <int O>
+__device__ __forceinline__ void load_regback(RegBack<O>& R, const float* __restrict__ flat) {
+    using D = MlpDims<kIn, O>;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+#pragma unroll
+        for (int o = 0; o < O; ++o) R.w3[o][q] = make_float2(flat[D::w3 + o * H + 2 * q], flat[D::w3 + o * H + 2 * q + 1]);
+#pragma unroll
+        for (int j = 0; j < H; ++j) R.w2[j][q] = make_float2(flat[D::w2 + j * H + 2 * q], flat[D::w2 + j * H + 2 * q + 1]);
+    }
+}
+// gA covers flat entries [D::w2, D::P): W2 | b2 | W3 | b3 as float2 (offset D::w2 / 2).
+template <int O, typename DY, int GN>
+__device__ __forceinline__ void bwd_regback(const RegBack<O>& R, const float2 (&h1)[3], const float2 (&h2)[3], DY dy,
+                                            float2 (&gA)[GN], float2 (&dz1)[3]) {
+    using D = MlpDims<kIn, O>;
+    constexpr int base = D::w2 / 2;
+    static_assert(GN >= (D::P + 1) / 2 - base, "accumulator too small");
+    float2 dh2[3], dh1[3];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) dh2[q] = dh1[q] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int o = 0; o < O; ++o) {
+        const float dyv = dy(o);
+        if (((D::b3 + o) & 1) == 0) gA[(D::b3 + o) / 2 - base].x += dyv; else gA[(D::b3 + o) / 2 - base].y += dyv;
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            gA[(D::w3 + o * H) / 2 + q - base] = __ffma2_rn(h2[q], bcast(dyv), gA[(D::w3 + o * H) / 2 + q - base]);
+            dh2[q] = __ffma2_rn(R.w3[o][q], bcast(dyv), dh2[q]);
+        }
+    }
+    float2 dz2[3];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        dz2[q] = make_float2(h2[q].x > 0.f ? dh2[q].x : 0.f, h2[q].y > 0.f ? dh2[q].y : 0.f);
+        gA[D::b2 / 2 + q - base].x += dz2[q].x;
+        gA[D::b2 / 2 + q - base].y += dz2[q].y;
+    }
+#pragma unroll
+    for (int j = 0; j < H; ++j) {
+        const float dz = half_of(dz2, j);
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            gA[(D::w2 + j * H) / 2 + q - base] = __ffma2_rn(h1[q], bcast(dz), gA[(D::w2 + j * H) / 2 + q - base]);
+            dh1[q] = __ffma2_rn(R.w2[j][q], bcast(dz), dh1[q]);
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 3; ++q) dz1[q] = make_float2(h1[q].x > 0.f ? dh1[q].x : 0.f, h1[q].y > 0.f ? dh1[q].y : 0.f);
+}
+// gB covers flat entries [0, D::w2): W1 | b1.
+__device__ __forceinline__ void accumulate_w1(const float (&x)[kIn], const float2 (&dz1)[3], float2 (&gB)[21]) {
+    const float2 x2[3] = {make_float2(x[0], x[1]), make_float2(x[2], x[3]), make_float2(x[4], x[5])};
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        gB[18 + q].x += dz1[q].x;
+        gB[18 + q].y += dz1[q].y;
+    }
+#pragma unroll
+    for (int j = 0; j < H; ++j) {
+        const float dz = half_of(dz1, j);
+#pragma unroll
+        for (int q = 0; q < 3; ++q) gB[j * 3 + q] = __ffma2_rn(x2[q], bcast(dz), gB[j * 3 + q]);
     }
 }
 

@@ -26,6 +26,7 @@
 namespace ia2c {
 int rollout_fused_supported(int N, int M);                                  // rollout_fused.cu
 int rollout_fused_launch(const ia2c_episode_desc* d, cudaStream_t s);
+int64_t rollout_fused_blocks(int64_t E, int N);
 
 namespace {
 
@@ -349,17 +350,29 @@ __device__ __forceinline__ void adam_update(float& p, float& m, float& v, float 
     p = p - step_size * (mi / (sqrtf(vi) / bc2_sqrt + 1e-8f));
 }
 
-// grid (N, ceil((P+1)/32)); block 256 = 32 entries x 8 slices of the partial blocks; fixed-order sums.
-__global__ void __launch_bounds__(256) reduce_adam_kernel(ReduceArgs R) {
+// grid (N, ceil((P+1)/32)); block 1024 = 32 entries x 32 slices of the partial blocks; fixed-order sums.
+// The partials are L2-resident, so a thread's chain of dependent adds costs one L2 round trip per term: many
+// short slices (<= 8 terms at 256 partial blocks, loads issued back to back) instead of few long ones.
+constexpr int kReduceSlices = 32;
+__global__ void __launch_bounds__(32 * kReduceSlices) reduce_adam_kernel(ReduceArgs R) {
     const int n = blockIdx.x, P = R.P;
     const int col = threadIdx.x & 31, slice = threadIdx.x >> 5;
     const int i = blockIdx.y * 32 + col;
-    __shared__ float part[8][33];
+    __shared__ float part[kReduceSlices][33];
     float s = 0.f;
     if (i <= P) {
         if (R.from_partials) {
             const float* src = R.partials + (int64_t)n * R.n_blocks * (P + 1) + i;
-            for (int b = slice; b < R.n_blocks; b += 8) s += src[(int64_t)b * (P + 1)];
+            float v[8];
+            for (int b0 = slice; b0 < R.n_blocks; b0 += 8 * kReduceSlices) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int b = b0 + u * kReduceSlices;
+                    v[u] = b < R.n_blocks ? src[(int64_t)b * (P + 1)] : 0.f;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) s += v[u];
+            }
         } else if (slice == 0) {
             s = R.grad[(int64_t)n * (P + 1) + i];
         }
@@ -368,7 +381,7 @@ __global__ void __launch_bounds__(256) reduce_adam_kernel(ReduceArgs R) {
     __syncthreads();
     if (slice != 0 || i > P) return;
 #pragma unroll
-    for (int k = 1; k < 8; ++k) s += part[k][col];
+    for (int k = 1; k < kReduceSlices; ++k) s += part[k][col];
     if (R.from_partials) {
         if (i == P) s *= R.loss_scale;
         R.grad[(int64_t)n * (P + 1) + i] = s;
@@ -418,9 +431,18 @@ int validate(const ia2c_episode_desc* d, const char* who) {
 
 using namespace ia2c;
 
+static bool fused_critic(const ia2c_episode_desc* d) {
+    return (d->flags & IA2C_FLAG_FUSED_ROLLOUT) && (d->flags & IA2C_FLAG_FUSED_CRITIC);
+}
+// partial rows per agent written by the critic-gradient producer (fused rollout stage or critic_grad_kernel)
+static int critic_partial_blocks(const ia2c_episode_desc* d) {
+    return fused_critic(d) ? (int)rollout_fused_blocks(d->E, d->N) : grad_blocks(d);
+}
+
 extern "C" size_t ia2c_episode_partials_floats(const ia2c_episode_desc* d) {
     if (!d || d->N < 1 || d->E < 1 || d->T < 1) return 0;
-    return (size_t)d->N * grad_blocks(d) * (kCriticP + 1);
+    const size_t blocks = (size_t)std::max<int64_t>(grad_blocks(d), rollout_fused_blocks(d->E, std::min(d->N, 8)));
+    return (size_t)d->N * blocks * (kCriticP + 1);
 }
 
 extern "C" int ia2c_rollout(const ia2c_episode_desc* d, void* stream) {
@@ -430,6 +452,10 @@ extern "C" int ia2c_rollout(const ia2c_episode_desc* d, void* stream) {
     cudaStream_t s = as_stream(stream);
     if (d->flags & IA2C_FLAG_FUSED_ROLLOUT) {
         IA2C_REQUIRE(rollout_fused_supported(d->N, d->M), "ia2c_rollout: IA2C_FLAG_FUSED_ROLLOUT needs N<=8 with M=5 (or N=2, M=3); got N=%d M=%d", d->N, d->M);
+        if (d->flags & IA2C_FLAG_FUSED_CRITIC) {
+            IA2C_REQUIRE(d->partials && d->partials_floats >= ia2c_episode_partials_floats(d) && d->critic_step,
+                         "ia2c_rollout: IA2C_FLAG_FUSED_CRITIC needs the partials workspace and critic_step");
+        }
         return rollout_fused_launch(d, s);
     }
     StepArgs S;
@@ -465,7 +491,7 @@ extern "C" int ia2c_rollout(const ia2c_episode_desc* d, void* stream) {
 static int run_reduce(const ia2c_episode_desc* d, int which, int from_partials, int apply, cudaStream_t s) {
     ReduceArgs R;
     R.partials = d->partials;
-    R.n_blocks = grad_blocks(d);
+    R.n_blocks = which == 0 ? critic_partial_blocks(d) : grad_blocks(d);
     R.P = which == 0 ? kCriticP : kActorP;
     R.grad = which == 0 ? d->critic_grad : d->actor_grad;
     R.grad_accum = which == 0 ? nullptr : d->actor_grad_accum;
@@ -483,7 +509,7 @@ static int run_reduce(const ia2c_episode_desc* d, int which, int from_partials, 
         if (int rc = check_launch("bump_steps_kernel")) return rc;
     }
     dim3 grid(d->N, ceil_div(R.P + 1, 32));
-    reduce_adam_kernel<<<grid, 256, 0, s>>>(R);
+    reduce_adam_kernel<<<grid, 32 * kReduceSlices, 0, s>>>(R);
     return check_launch("reduce_adam_kernel");
 }
 
@@ -498,9 +524,11 @@ extern "C" int ia2c_critic_phase(const ia2c_episode_desc* d, void* stream) {
     if (int rc = validate(d, "ia2c_critic_phase")) return rc;
     if (int rc = check_update_ptrs(d, "ia2c_critic_phase")) return rc;
     cudaStream_t s = as_stream(stream);
-    dim3 grid(grad_blocks(d), d->N);
-    critic_grad_kernel<<<grid, kGradThreads, 0, s>>>(*d, d->partials);
-    if (int rc = check_launch("critic_grad_kernel")) return rc;
+    if (!fused_critic(d)) {   // otherwise the rollout kernel's critic stage already wrote the partials
+        dim3 grid(grad_blocks(d), d->N);
+        critic_grad_kernel<<<grid, kGradThreads, 0, s>>>(*d, d->partials);
+        if (int rc = check_launch("critic_grad_kernel")) return rc;
+    }
     return run_reduce(d, 0, 1, !(d->flags & IA2C_FLAG_SKIP_ADAM), s);
 }
 
@@ -635,7 +663,7 @@ extern "C" int ia2c_train_episode_timed(const ia2c_episode_desc* d, float* host_
     cudaEventRecord(ev[0], s);
     rc = ia2c_rollout(d, stream);
     cudaEventRecord(ev[1], s);
-    if (!rc) { critic_grad_kernel<<<grid, kGradThreads, 0, s>>>(*d, d->partials); rc = check_launch("critic_grad_kernel"); }
+    if (!rc && !fused_critic(d)) { critic_grad_kernel<<<grid, kGradThreads, 0, s>>>(*d, d->partials); rc = check_launch("critic_grad_kernel"); }
     cudaEventRecord(ev[2], s);
     if (!rc) rc = run_reduce(d, 0, 1, apply, s);
     cudaEventRecord(ev[3], s);

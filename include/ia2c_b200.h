@@ -206,6 +206,8 @@ typedef struct ia2c_episode_desc {
 } ia2c_episode_desc;
 
 #define IA2C_FLAG_FUSED_ROLLOUT 1   /* use the persistent one-launch rollout kernel (N <= 8) */
+#define IA2C_FLAG_FUSED_CRITIC  4   /* with FUSED_ROLLOUT: the rollout kernel also accumulates the critic gradient
+                                       (ia2c_critic_phase then only reduces the partials and applies Adam) */
 #define IA2C_FLAG_SKIP_ADAM     2   /* stop after writing gradients (multi-GPU: all-reduce, then ia2c_adam_step) */
 
 size_t ia2c_episode_partials_floats(const ia2c_episode_desc* d);

@@ -1,12 +1,18 @@
-import sys; sys.path.insert(0,'/root/repo')
-import numpy as np, torch
-from ia2c_b200.trainer import IA2CTrainer, reference_init
-for (E,N,fused) in ((4096,2,True),(1024,64,False)):
-    tr=IA2CTrainer(E,n_agents=N,init=reference_init(N,5,seed=0),seed=7,fused_rollout=fused)
-    for _ in range(5): tr.train_episode()
-    acc={}
-    n=30
+"""Warm per-kernel durations (CUDA events between the kernels, ia2c_train_episode_timed)."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from ia2c_b200.trainer import IA2CTrainer, reference_init  # noqa: E402
+
+configs = [(4096, 2, True, True), (4096, 2, True, False), (4096, 2, False, False), (1024, 64, False, False)]
+for (E, N, fused, fc) in configs:
+    tr = IA2CTrainer(E, n_agents=N, init=reference_init(N, 5, seed=0), seed=7, fused_rollout=fused, fused_critic=fc)
+    for _ in range(5):
+        tr.train_episode()
+    acc, n = {}, 30
     for _ in range(n):
-        r=tr.train_episode_timed()
-        for k,v in r.items(): acc[k]=acc.get(k,0)+v/n
-    print(E,N,{k:round(v*1000,2) for k,v in acc.items()}, "us")
+        for k, v in tr.train_episode_timed().items():
+            acc[k] = acc.get(k, 0) + v / n
+    print(f"E={E} N={N} fused_rollout={fused} fused_critic={fc}", {k: round(v * 1000, 2) for k, v in acc.items()}, "us",
+          "total", round(sum(acc.values()) * 1000, 1))
