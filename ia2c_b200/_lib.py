@@ -17,6 +17,7 @@ i32, i64, u32, u64, f32, f64 = C.c_int32, C.c_int64, C.c_uint32, C.c_uint64, C.c
 FLAG_FUSED_ROLLOUT = 1
 FLAG_SKIP_ADAM = 2
 FLAG_FUSED_CRITIC = 4
+FLAG_GRAD_ONLY = 8
 BELIEF_RECORD = 8
 ACTOR_P = 105
 CRITIC_P = 147
@@ -46,6 +47,11 @@ class EpisodeDesc(C.Structure):
     ]
 
 
+class PeerDesc(C.Structure):
+    """Mirror of ``ia2c_peer_desc``."""
+    _fields_ = [("rank", i32), ("world", i32), ("inbox", vp * 8), ("flags", vp * 8), ("error", vp)]
+
+
 _DP = C.POINTER(EpisodeDesc)
 
 # name -> (restype, argtypes); every symbol declared in include/ia2c_b200.h
@@ -72,6 +78,9 @@ SIGNATURES = {
     "ia2c_critic_phase": (C.c_int, [_DP, vp]),
     "ia2c_actor_phase": (C.c_int, [_DP, vp]),
     "ia2c_apply_adam": (C.c_int, [_DP, i32, vp]),
+    "ia2c_peer_inbox_floats": (C.c_size_t, [_DP, i32]),
+    "ia2c_peer_flag_words": (C.c_size_t, [_DP, i32]),
+    "ia2c_allreduce_adam": (C.c_int, [_DP, i32, C.POINTER(PeerDesc), u32, i32, vp]),
     "ia2c_train_episode": (C.c_int, [_DP, vp]),
     "ia2c_train_episode_host": (C.c_int, [_DP, vp, vp, vp, vp, vp]),
     "ia2c_train_episode_timed": (C.c_int, [_DP, vp, vp]),

@@ -513,6 +513,111 @@ static int run_reduce(const ia2c_episode_desc* d, int which, int from_partials, 
     return check_launch("reduce_adam_kernel");
 }
 
+// ------------------------------------------------------------------------------------------------
+// Fused gradient all-reduce + Adam over NVLink peer memory (multi-GPU, one process per GPU).
+//
+// Per optimiser phase every rank holds locally summed gradients (already scaled by the GLOBAL 1/(T*E_total)).
+// Instead of reduce kernel -> NCCL all-reduce -> Adam kernel (three launches and a ~20 us small-message
+// collective), ONE kernel per rank does all of it over peer-mapped ("symmetric") buffers:
+//   1. sum this rank's per-block partials for a chunk of 32 entries              (fixed order)
+//   2. PUSH the 32 sums into every peer's inbox slot [parity][my rank]           (plain stores over NVLink)
+//   3. system-scope fence, then raise flag[chunk][my rank] = epoch on every peer
+//   4. spin (bounded) until flag[chunk][r] == epoch for every rank r
+//   5. add the world's contributions in RANK order (every rank computes bit-identical sums) and apply Adam.
+// Chunks are independent, so transfer and arithmetic of different chunks overlap; the grid is persistent
+// (<= one resident wave) so a block never waits for a peer block that cannot be scheduled.  Inboxes are
+// double-buffered by epoch parity: a peer can be at most one exchange ahead of this rank.
+struct PeerArgs {
+    int rank, world;
+    float* inbox[8];
+    uint32_t* flags[8];
+    int32_t* error;
+    uint32_t epoch;
+    int t;                       // Adam step number of this update (host-tracked in the multi-rank path)
+    int64_t inbox_base, stride;  // float offset of this phase's region; floats per (parity, rank) slot = N * (P+1)
+    int64_t flag_base;           // word offset of this phase's flags
+};
+
+__global__ void __launch_bounds__(32 * kReduceSlices) allreduce_adam_kernel(ReduceArgs R, PeerArgs X, int total_chunks,
+                                                                            int chunks_per_agent) {
+    __shared__ float part[kReduceSlices][33];
+    __shared__ int timeout;
+    const int P = R.P, col = threadIdx.x & 31, slice = threadIdx.x >> 5;
+    const int parity = (int)(X.epoch & 1u);
+    if (threadIdx.x == 0) timeout = 0;
+    for (int c = blockIdx.x; c < total_chunks; c += gridDim.x) {
+        const int n = c / chunks_per_agent, i = (c % chunks_per_agent) * 32 + col;
+        float s = 0.f;
+        if (i <= P) {
+            const float* src = R.partials + (int64_t)n * R.n_blocks * (P + 1) + i;
+            float v[8];
+            for (int b0 = slice; b0 < R.n_blocks; b0 += 8 * kReduceSlices) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int b = b0 + u * kReduceSlices;
+                    v[u] = b < R.n_blocks ? src[(int64_t)b * (P + 1)] : 0.f;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) s += v[u];
+            }
+        }
+        part[slice][col] = s;
+        __syncthreads();
+        const int64_t idx = (int64_t)n * (P + 1) + i;
+        if (slice == 0 && i <= P) {
+#pragma unroll
+            for (int k = 1; k < kReduceSlices; ++k) s += part[k][col];
+            if (i == P) s *= R.loss_scale;
+            const int64_t slot = X.inbox_base + ((int64_t)parity * X.world + X.rank) * X.stride + idx;
+            for (int p = 0; p < X.world; ++p) X.inbox[p][slot] = s;          // NVLink stores (self included)
+            __threadfence_system();
+        }
+        __syncthreads();
+        if (threadIdx.x < X.world) {                                         // one signalling/waiting thread per peer
+            const int p = threadIdx.x;
+            const int64_t f = X.flag_base + (int64_t)c * X.world;
+            *(volatile uint32_t*)(X.flags[p] + f + X.rank) = X.epoch;        // raise my flag on peer p
+            volatile uint32_t* mine = X.flags[X.rank] + f + p;               // wait for peer p's flag on me
+            int spins = 0;
+            while (*mine != X.epoch) {
+                __nanosleep(64);
+                if (++spins > (1 << 22)) { timeout = 1; break; }             // ~ 0.3 s: report instead of hanging
+            }
+            __threadfence_system();
+        }
+        __syncthreads();
+        if (slice == 0 && i <= P) {
+            float g = 0.f;
+            for (int r = 0; r < X.world; ++r)                                // rank order: identical sums on every rank
+                g += __ldcv(X.inbox[X.rank] + X.inbox_base + ((int64_t)parity * X.world + r) * X.stride + idx);
+            R.grad[idx] = g;
+            if (i == P) {
+                R.loss_out[n] = g;
+                R.step[n] = X.t;                                             // device-side counter follows the host's
+            } else {
+                const int64_t k = (int64_t)n * P + i;
+                if (R.grad_accum) {                                          // actor gradients accumulate (Q2)
+                    g += R.grad_accum[k];
+                    R.grad_accum[k] = g;
+                }
+                adam_update(R.params[k], R.m[k], R.v[k], g, X.t, R.lr);
+            }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && timeout && X.error) *X.error = 1;
+}
+
+static void phase_regions(const ia2c_episode_desc* d, int world, int which, int64_t& inbox_base, int64_t& stride,
+                          int64_t& flag_base, int& chunks_per_agent) {
+    const int64_t stride_c = (int64_t)d->N * (kCriticP + 1), stride_a = (int64_t)d->N * (kActorP + 1);
+    const int chunks_c = ceil_div(kCriticP + 1, 32), chunks_a = ceil_div(kActorP + 1, 32);
+    inbox_base = which == 0 ? 0 : 2 * world * stride_c;
+    stride = which == 0 ? stride_c : stride_a;
+    flag_base = which == 0 ? 0 : (int64_t)d->N * chunks_c * world;
+    chunks_per_agent = which == 0 ? chunks_c : chunks_a;
+}
+
 static int check_update_ptrs(const ia2c_episode_desc* d, const char* who) {
     IA2C_REQUIRE(d->partials && d->partials_floats >= ia2c_episode_partials_floats(d), "%s: partials workspace too small", who);
     IA2C_REQUIRE(d->critic_grad && d->actor_grad && d->critic_m && d->critic_v && d->actor_m && d->actor_v &&
@@ -529,6 +634,7 @@ extern "C" int ia2c_critic_phase(const ia2c_episode_desc* d, void* stream) {
         critic_grad_kernel<<<grid, kGradThreads, 0, s>>>(*d, d->partials);
         if (int rc = check_launch("critic_grad_kernel")) return rc;
     }
+    if (d->flags & IA2C_FLAG_GRAD_ONLY) return 0;
     return run_reduce(d, 0, 1, !(d->flags & IA2C_FLAG_SKIP_ADAM), s);
 }
 
@@ -539,6 +645,7 @@ extern "C" int ia2c_actor_phase(const ia2c_episode_desc* d, void* stream) {
     dim3 grid(grad_blocks(d), d->N);
     actor_grad_kernel<<<grid, kGradThreads, 0, s>>>(*d, d->partials);
     if (int rc = check_launch("actor_grad_kernel")) return rc;
+    if (d->flags & IA2C_FLAG_GRAD_ONLY) return 0;
     return run_reduce(d, 1, 1, !(d->flags & IA2C_FLAG_SKIP_ADAM), s);
 }
 
@@ -675,4 +782,57 @@ extern "C" int ia2c_train_episode_timed(const ia2c_episode_desc* d, float* host_
     for (int i = 0; i < 5 && !rc; ++i) cudaEventElapsedTime(&host_ms_out[i], ev[i], ev[i + 1]);
     for (auto& e : ev) cudaEventDestroy(e);
     return rc;
+}
+
+extern "C" size_t ia2c_peer_inbox_floats(const ia2c_episode_desc* d, int32_t world) {
+    if (!d || world < 1) return 0;
+    return (size_t)2 * world * d->N * ((kCriticP + 1) + (kActorP + 1));
+}
+extern "C" size_t ia2c_peer_flag_words(const ia2c_episode_desc* d, int32_t world) {
+    if (!d || world < 1) return 0;
+    return (size_t)d->N * (ceil_div(kCriticP + 1, 32) + ceil_div(kActorP + 1, 32)) * world;
+}
+
+extern "C" int ia2c_allreduce_adam(const ia2c_episode_desc* d, int32_t which, const ia2c_peer_desc* peers, uint32_t epoch,
+                                   int32_t adam_step, void* stream) {
+    if (int rc = validate(d, "ia2c_allreduce_adam")) return rc;
+    if (int rc = check_update_ptrs(d, "ia2c_allreduce_adam")) return rc;
+    IA2C_REQUIRE(which == 0 || which == 1, "ia2c_allreduce_adam: which=%d", which);
+    IA2C_REQUIRE(peers && peers->world >= 1 && peers->world <= 8 && peers->rank >= 0 && peers->rank < peers->world,
+                 "ia2c_allreduce_adam: bad peer descriptor");
+    IA2C_REQUIRE(epoch > 0 && adam_step > 0, "ia2c_allreduce_adam: epoch and adam_step start at 1");
+    for (int p = 0; p < peers->world; ++p)
+        IA2C_REQUIRE(peers->inbox[p] && peers->flags[p], "ia2c_allreduce_adam: null peer buffer %d", p);
+    cudaStream_t s = as_stream(stream);
+    ReduceArgs R;
+    R.partials = d->partials;
+    R.n_blocks = which == 0 ? critic_partial_blocks(d) : grad_blocks(d);
+    R.P = which == 0 ? kCriticP : kActorP;
+    R.grad = which == 0 ? d->critic_grad : d->actor_grad;
+    R.grad_accum = which == 0 ? nullptr : d->actor_grad_accum;
+    R.params = which == 0 ? d->critic_params : d->actor_params;
+    R.m = which == 0 ? d->critic_m : d->actor_m;
+    R.v = which == 0 ? d->critic_v : d->actor_v;
+    R.step = which == 0 ? d->critic_step : d->actor_step;
+    R.loss_out = d->loss_out + (which == 0 ? 0 : d->N);
+    R.loss_scale = 1.f / (float)((int64_t)d->T * d->E_total);
+    R.lr = which == 0 ? d->lr_critic : d->lr_actor;
+    R.apply_adam = 1;
+    R.from_partials = 1;
+    PeerArgs X;
+    X.rank = peers->rank;
+    X.world = peers->world;
+    for (int p = 0; p < 8; ++p) {
+        X.inbox[p] = p < peers->world ? peers->inbox[p] : nullptr;
+        X.flags[p] = p < peers->world ? peers->flags[p] : nullptr;
+    }
+    X.error = peers->error;
+    X.epoch = epoch;
+    X.t = adam_step;
+    int chunks_per_agent;
+    phase_regions(d, peers->world, which, X.inbox_base, X.stride, X.flag_base, chunks_per_agent);
+    const int total = d->N * chunks_per_agent;
+    const int grid = std::min(total, kSMs);          // persistent: every block is resident
+    allreduce_adam_kernel<<<grid, 32 * kReduceSlices, 0, s>>>(R, X, total, chunks_per_agent);
+    return check_launch("allreduce_adam_kernel");
 }

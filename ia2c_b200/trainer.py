@@ -50,7 +50,7 @@ class IA2CTrainer:
     def __init__(self, num_envs, n_agents=2, n_models=5, steps_per_episode=30, max_episode_steps=30,
                  lr_critic=0.0002, lr_actor=0.0001, beta=0.001, gamma=0.9, seed=0, device=None,
                  rank=0, world_size=1, process_group=None, dumps=False, fused_rollout=False, fused_critic=None,
-                 init=None):
+                 init=None, comm="auto"):
         _lib.require_cuda()
         self.lib = _lib.load()
         self.rank, self.world = int(rank), int(world_size)
@@ -116,6 +116,48 @@ class IA2CTrainer:
         if init is None:
             init = reference_init(N, M)
         self.load_init(*init)
+        self.comm = "none"
+        if self.world > 1:
+            self._setup_comm(comm)
+
+    # ------------------------------------------------------------------ multi-GPU exchange
+    def _setup_comm(self, comm):
+        """comm="p2p": fused all-reduce + Adam kernel over NVLink peer memory (torch symmetric memory provides the
+        peer mappings, the exchange itself is ia2c_allreduce_adam); comm="nccl": reduce -> NCCL all-reduce -> Adam.
+        "auto" tries p2p and falls back to NCCL if symmetric memory cannot be set up."""
+        import torch.distributed as dist
+
+        if comm in ("auto", "p2p") and self.world <= 8:
+            try:
+                import torch.distributed._symmetric_memory as symm
+
+                group = self.pg if self.pg is not None else dist.group.WORLD
+                n_f = int(self.lib.ia2c_peer_inbox_floats(C.byref(self.desc), self.world))
+                n_w = int(self.lib.ia2c_peer_flag_words(C.byref(self.desc), self.world))
+                self._inbox = symm.empty(n_f, dtype=torch.float32, device=self.device)
+                self._flags = symm.empty(n_w, dtype=torch.int32, device=self.device)
+                self._inbox.zero_()
+                self._flags.zero_()
+                h_in = symm.rendezvous(self._inbox, group)
+                h_fl = symm.rendezvous(self._flags, group)
+                self._comm_error = torch.zeros(1, dtype=torch.int32, device=self.device)
+                self.peers = _lib.PeerDesc()
+                self.peers.rank, self.peers.world = self.rank, self.world
+                for p in range(self.world):
+                    self.peers.inbox[p] = int(h_in.buffer_ptrs[p])
+                    self.peers.flags[p] = int(h_fl.buffer_ptrs[p])
+                self.peers.error = self._comm_error.data_ptr()
+                self._symm_handles = (h_in, h_fl)
+                torch.cuda.synchronize(self.device)
+                dist.barrier(group=self.pg)      # every rank's flags are zero before anyone raises one
+                self.comm = "p2p"
+                self._epoch = 0
+                self.desc.flags |= _lib.FLAG_GRAD_ONLY
+                return
+            except Exception as exc:  # symmetric memory unavailable: NCCL path
+                if comm == "p2p":
+                    raise _lib.IA2CError(f"comm='p2p' requested but symmetric memory setup failed: {exc}") from exc
+        self.comm = "nccl"
 
     # ------------------------------------------------------------------ parameters
     def load_init(self, actor, critic, filter_action):
@@ -156,6 +198,15 @@ class IA2CTrainer:
     def update(self):
         d, s = C.byref(self.desc), self._stream()
         with torch.cuda.device(self.device):
+            if self.comm == "p2p":
+                step = self.episode + 1          # one Adam step per net per episode
+                _lib.check(self.lib.ia2c_critic_phase(d, s), "ia2c_critic_phase")      # gradient partials only
+                self._epoch += 1
+                _lib.check(self.lib.ia2c_allreduce_adam(d, 0, C.byref(self.peers), self._epoch, step, s), "ia2c_allreduce_adam(critic)")
+                _lib.check(self.lib.ia2c_actor_phase(d, s), "ia2c_actor_phase")
+                self._epoch += 1
+                _lib.check(self.lib.ia2c_allreduce_adam(d, 1, C.byref(self.peers), self._epoch, step, s), "ia2c_allreduce_adam(actor)")
+                return
             _lib.check(self.lib.ia2c_critic_phase(d, s), "ia2c_critic_phase")
             if self.world > 1:
                 self._allreduce(self.critic_grad)
@@ -279,7 +330,13 @@ class IA2CTrainer:
         self.episode += 1
         return dict(zip(("rollout", "critic_grad", "critic_reduce_adam", "actor_grad", "actor_reduce_adam"), list(ms)))
 
+    def check_comm(self):
+        """Raise if a peer failed to arrive in a fused all-reduce (the kernel times out instead of hanging)."""
+        if self.comm == "p2p" and int(self._comm_error.item()):
+            raise _lib.IA2CError("ia2c_allreduce_adam: a peer rank did not arrive within the spin budget")
+
     def read_stats(self):
+        self.check_comm()
         self._h_loss.copy_(self.loss_out, non_blocking=True)
         self._h_return.copy_(self.ep_return, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()

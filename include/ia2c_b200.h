@@ -208,6 +208,8 @@ typedef struct ia2c_episode_desc {
 #define IA2C_FLAG_FUSED_ROLLOUT 1   /* use the persistent one-launch rollout kernel (N <= 8) */
 #define IA2C_FLAG_FUSED_CRITIC  4   /* with FUSED_ROLLOUT: the rollout kernel also accumulates the critic gradient
                                        (ia2c_critic_phase then only reduces the partials and applies Adam) */
+#define IA2C_FLAG_GRAD_ONLY     8   /* critic/actor phase stop after the gradient kernel (per-block partials only);
+                                       ia2c_allreduce_adam then reduces, exchanges and steps */
 #define IA2C_FLAG_SKIP_ADAM     2   /* stop after writing gradients (multi-GPU: all-reduce, then ia2c_adam_step) */
 
 size_t ia2c_episode_partials_floats(const ia2c_episode_desc* d);
@@ -222,6 +224,24 @@ int ia2c_critic_phase(const ia2c_episode_desc* d, void* stream);
 int ia2c_actor_phase(const ia2c_episode_desc* d, void* stream);
 /* Adam from the gradient buffers (after a multi-GPU all-reduce): which = 0 critics, 1 actors. */
 int ia2c_apply_adam(const ia2c_episode_desc* d, int32_t which, void* stream);
+/* Multi-GPU: fused gradient all-reduce + Adam over NVLink peer memory, ONE kernel per optimiser phase instead of
+ * reduce -> NCCL all-reduce -> Adam.  Run it after the phase's gradient kernel (ia2c_rollout with
+ * IA2C_FLAG_FUSED_CRITIC, or ia2c_critic_phase / ia2c_actor_phase with IA2C_FLAG_SKIP_ADAM ... see trainer.py).
+ * inbox[p] / flags[p] are rank p's symmetric buffers mapped into this process (ia2c_peer_inbox_floats floats,
+ * ia2c_peer_flag_words zero-initialised 32-bit words).  epoch increases by one per call on every rank (same value
+ * on all ranks); adam_step is the Adam step number of this update.  Every rank must launch it; *error is set to 1
+ * if a peer does not arrive within the spin budget (the kernel then returns instead of hanging). */
+typedef struct ia2c_peer_desc {
+    int32_t rank, world;       /* world <= 8 (one NVSwitch domain) */
+    float* inbox[8];
+    uint32_t* flags[8];
+    int32_t* error;            /* device int32, may be NULL */
+} ia2c_peer_desc;
+size_t ia2c_peer_inbox_floats(const ia2c_episode_desc* d, int32_t world);
+size_t ia2c_peer_flag_words(const ia2c_episode_desc* d, int32_t world);
+int ia2c_allreduce_adam(const ia2c_episode_desc* d, int32_t which, const ia2c_peer_desc* peers, uint32_t epoch,
+                        int32_t adam_step, void* stream);
+
 /* rollout + critic phase + actor phase on one stream. */
 int ia2c_train_episode(const ia2c_episode_desc* d, void* stream);
 /* Same, with HOST buffers: copies the injected uniforms host->device, runs the episode, copies

@@ -21,27 +21,31 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ok = True
-    for N, E_total, fused in ((2, 64 * world, True), (3, 16 * world, False)):
+    for N, E_total, fused, comm in ((2, 64 * world, True, "p2p"), (3, 16 * world, False, "p2p"), (2, 64 * world, True, "nccl"),
+                                    (5, 8 * world, True, "p2p")):
         init = reference_init(N, 5, seed=3)
-        sharded = IA2CTrainer(E_total, n_agents=N, init=init, seed=11, rank=rank, world_size=world, fused_rollout=fused, dumps=True)
+        sharded = IA2CTrainer(E_total, n_agents=N, init=init, seed=11, rank=rank, world_size=world, fused_rollout=fused, dumps=True,
+                              comm=comm)
+        assert sharded.comm == comm, (sharded.comm, comm)
         single = IA2CTrainer(E_total, n_agents=N, init=init, seed=11, fused_rollout=fused, dumps=True)
         for ep in range(3):
             sharded.train_episode()
             single.train_episode()
         torch.cuda.synchronize()
+        sharded.check_comm()
         sl = slice(sharded.env_offset, sharded.env_offset + sharded.E)
         h = lambda t: t.detach().cpu().numpy()
         for name in ("obs", "reward", "act", "partner_pred", "partner_true", "belief_dump"):
             a, b = h(getattr(sharded, name)), h(getattr(single, name))[:, sl]
             if not np.array_equal(a, b):
                 ok = False
-                print(f"[rank {rank}] N={N} {name} differs from the single-rank run")
+                print(f"[rank {rank}] N={N} comm={comm} {name} differs from the single-rank run")
         for name in ("actor_params", "critic_params", "actor_grad_accum"):
             a, b = h(getattr(sharded, name)).astype(np.float64), h(getattr(single, name)).astype(np.float64)
             err = np.abs(a - b).max() / np.abs(b).max()
             if err > 1e-6:
                 ok = False
-                print(f"[rank {rank}] N={N} {name} rel err {err:.2e}")
+                print(f"[rank {rank}] N={N} comm={comm} {name} rel err {err:.2e}")
         # every rank holds identical parameters after the all-reduce + Adam
         p = sharded.actor_params.clone()
         dist.broadcast(p, 0)
