@@ -11,3 +11,32 @@ STATE_VISIBLE = False
 MEM = True
 STATE = False
 LSTM = False
+
+
+def _route_make_vec():
+    """With the REAL gymnasium installed, ``gym.make_vec("Org-v0", num_envs=E)`` (ia2c.py:42) would spawn E worker
+    processes around single-env instances.  Route ids whose entry point is this drop-in ``Org`` to the batched GPU
+    env instead; every other id keeps gymnasium's behaviour."""
+    try:
+        import gymnasium as gym
+    except Exception:
+        return
+    if getattr(gym, "__version__", "").endswith("ia2c_b200.shim") or getattr(gym.make_vec, "_ia2c_routed", False):
+        return
+    original = gym.make_vec
+
+    def make_vec(id, num_envs=1, *args, **kwargs):
+        try:
+            spec = gym.spec(id) if isinstance(id, str) else id
+            entry = spec.entry_point
+            if entry == "Org:Org" or entry is Org:
+                return OrgVecEnv(num_envs, n_agents=2, max_episode_steps=spec.max_episode_steps)
+        except Exception:
+            pass
+        return original(id, num_envs, *args, **kwargs)
+
+    make_vec._ia2c_routed = True
+    gym.make_vec = make_vec
+
+
+_route_make_vec()

@@ -353,6 +353,40 @@ class IA2CTrainer:
                     critic_loss_window=np.mean(self.critic_losses, axis=0),
                     actor_loss_window=np.mean(self.actor_losses, axis=0), mean_return=np.mean(self.reward_lst))
 
+    # ------------------------------------------------------------------ checkpoint / resume
+    _CKPT_TENSORS = ("actor_params", "critic_params", "actor_grad_accum", "actor_m", "actor_v", "critic_m", "critic_v",
+                     "actor_step", "critic_step", "filter_action", "env_state", "env_hist", "env_cls", "env_elapsed",
+                     "belief_records")
+
+    def state_dict(self):
+        """Everything a resumed run needs to continue bit-identically: network parameters, Adam moments and step
+        counters, the actor's never-zeroed gradient accumulators, the belief models, env and belief
+        state, the episode counter that keys the Philox streams, and the loss / return windows that ia2c.py prints
+        (the reference has no checkpointing; SURVEY.md §5 lists this state)."""
+        torch.cuda.current_stream(self.device).synchronize()
+        sd = {k: getattr(self, k).detach().cpu().clone() for k in self._CKPT_TENSORS}
+        sd.update(episode=self.episode, seed=self.seed, dims=(self.E_total, self.E, self.N, self.M, self.T),
+                  rank=self.rank, world=self.world, critic_losses=list(self.critic_losses),
+                  actor_losses=list(self.actor_losses), reward_lst=list(self.reward_lst))
+        return sd
+
+    def load_state_dict(self, sd):
+        if tuple(sd["dims"]) != (self.E_total, self.E, self.N, self.M, self.T) or sd["world"] != self.world:
+            raise ValueError(f"checkpoint is for dims/world {sd['dims']}/{sd['world']}, "
+                             f"trainer has {(self.E_total, self.E, self.N, self.M, self.T)}/{self.world}")
+        for k in self._CKPT_TENSORS:
+            getattr(self, k).copy_(sd[k])
+        self.episode, self.seed = int(sd["episode"]), int(sd["seed"])
+        self.desc.seed = self.seed
+        self.critic_losses, self.actor_losses = list(sd["critic_losses"]), list(sd["actor_losses"])
+        self.reward_lst = list(sd["reward_lst"])
+
+    def save(self, path):
+        torch.save(self.state_dict(), path)
+
+    def load(self, path):
+        self.load_state_dict(torch.load(path, map_location="cpu", weights_only=False))
+
     # ------------------------------------------------------------------ accounting
     def agent_steps_per_episode(self):
         return self.E_total * self.N * self.T

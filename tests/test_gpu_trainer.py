@@ -198,3 +198,23 @@ def test_pipelined_host_episodes_match_sequential_calls():
         assert np.array_equal(p["ep_return"], q["ep_return"]) and np.array_equal(p["critic_loss"], q["critic_loss"])
         assert np.array_equal(p["actor_loss"], q["actor_loss"])
     assert np.array_equal(host(a.actor_params), host(b.actor_params)) and a.episode == b.episode == n
+
+
+@pytest.mark.parametrize("fused", [False, True])
+def test_checkpoint_resume_is_bit_identical(tmp_path, fused):
+    E, N, M = 48, 2, 5
+    init = _random_init(N, M, seed=2)
+    a = make_trainer(E, N, M, init, seed=21, fused_rollout=fused)
+    for _ in range(3):
+        a.train_episode(sync_stats=True)
+    path = str(tmp_path / "ckpt.pt")
+    a.save(path)
+    b = make_trainer(E, N, M, _random_init(N, M, seed=99), seed=0, fused_rollout=fused)   # different init, different seed
+    b.load(path)
+    for _ in range(3):
+        sa = a.train_episode(sync_stats=True)
+        sb = b.train_episode(sync_stats=True)
+    for name in ("actor_params", "critic_params", "actor_grad_accum", "actor_m", "critic_v", "act", "obs", "belief_records"):
+        assert np.array_equal(host(getattr(a, name)), host(getattr(b, name))), name
+    assert int(b.actor_step[0]) == 6 and b.episode == 6
+    assert np.array_equal(sa["critic_loss_window"], sb["critic_loss_window"]) and sa["mean_return"] == sb["mean_return"]
