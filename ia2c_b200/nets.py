@@ -46,16 +46,18 @@ class _MLPFunction(torch.autograd.Function):
         x2 = x.detach().reshape(-1, state_dim).to(torch.float32).contiguous()
         rows = x2.shape[0]
         y = torch.empty(rows, action_dim, dtype=torch.float32, device=x2.device)
-        _lib.check(lib.ia2c_mlp_forward(_lib.ptr(flat.detach()), _lib.ptr(x2), _lib.ptr(y), rows, state_dim,
+        # keep the layer-1 activations when a backward pass may follow: it then never re-reads x to recompute them
+        h1 = torch.empty(rows, hidden_size, dtype=torch.float32, device=x2.device) if torch.is_grad_enabled() else None
+        _lib.check(lib.ia2c_mlp_forward(_lib.ptr(flat.detach()), _lib.ptr(x2), _lib.ptr(y), _lib.ptr(h1), rows, state_dim,
                                         action_dim, 1, int(softmax), _lib.stream_ptr()), "ia2c_mlp_forward")
-        ctx.save_for_backward(x2, flat)
+        ctx.save_for_backward(x2, flat, h1)
         ctx.dims = (state_dim, action_dim, softmax, tuple(x.shape))
         return y.reshape(*x.shape[:-1], action_dim)
 
     @staticmethod
     def backward(ctx, gy):
         lib = _lib.load()
-        x2, flat = ctx.saved_tensors
+        x2, flat, h1 = ctx.saved_tensors
         state_dim, action_dim, softmax, xshape = ctx.dims
         rows = x2.shape[0]
         dy = gy.reshape(rows, action_dim).to(torch.float32).contiguous()
@@ -63,7 +65,7 @@ class _MLPFunction(torch.autograd.Function):
         dx = torch.empty_like(x2) if ctx.needs_input_grad[0] else None
         ws = torch.empty(lib.ia2c_mlp_backward_workspace(rows, state_dim, action_dim), dtype=torch.float32,
                          device=x2.device)
-        _lib.check(lib.ia2c_mlp_backward(_lib.ptr(flat.detach()), _lib.ptr(x2), _lib.ptr(dy), _lib.ptr(grad),
+        _lib.check(lib.ia2c_mlp_backward(_lib.ptr(flat.detach()), _lib.ptr(x2), _lib.ptr(dy), _lib.ptr(h1), _lib.ptr(grad),
                                          _lib.ptr(dx), _lib.ptr(ws), rows, state_dim, action_dim, int(softmax), 0,
                                          _lib.stream_ptr()), "ia2c_mlp_backward")
         return (dx.reshape(xshape) if dx is not None else None), grad, None, None, None

@@ -71,14 +71,19 @@ class OrgVecEnv:
         self.truncated = torch.zeros(E, dtype=torch.uint8, device=dev)
         self.single_observation_space = _Box(-np.ones(6), np.ones(6))
         self.single_action_space = _Discrete(2)
-        self.reset()
+        self.reset_device()
 
-    def reset(self, seed=None, options=None):
+    def reset_device(self):
+        """Reset all envs; returns the device observation tensor f32[E,6] (no host sync)."""
         with self._guard():
             _lib.check(self.lib.ia2c_org_reset(_lib.ptr(self.state), _lib.ptr(self.hist), _lib.ptr(self.cls),
                                                _lib.ptr(self.elapsed), _lib.ptr(self.obs), self.num_envs,
                                                _lib.stream_ptr()), "ia2c_org_reset")
-        return self.obs, {}
+        return self.obs
+
+    def reset(self, seed=None, options=None):
+        """gymnasium vector-env signature: (float32 numpy observations [E,6], info)."""
+        return self.reset_device().cpu().numpy(), {}
 
     def _guard(self):
         import torch
@@ -199,7 +204,7 @@ class Org(_EnvBase):
         return (self.observation, self._reward, self.done, self.done, {})
 
     def reset(self, seed=None, options={}):
-        self._vec.reset()
+        self._vec.reset_device()
         self._state = RESET_STATE
         self.done = False
         self._reward = 0

@@ -109,16 +109,19 @@ int ia2c_debug_divide(const double* a, const double* b, double* q_seq, double* q
 /* ------------------------------------------------------------------ (3) actor / critic MLPs -- */
 /* NeuralNet.forward (ac_nets.py:34-41) for `nets` independent networks over the same rows:
  *   params float[nets,P]; x float[rows,F] (shared by all nets) -> y float[nets,rows,O];
- *   softmax != 0 applies the actor's softmax.  F arbitrary, O <= 16. */
-int ia2c_mlp_forward(const float* params, const float* x, float* y, int64_t rows, int32_t F, int32_t O,
+ *   softmax != 0 applies the actor's softmax.  F arbitrary, O <= 32.
+ *   h1_out float[rows,6] (may be NULL; nets == 1 only): the post-ReLU layer-1 activations, kept so that the
+ *   backward pass does not have to read x again to recompute them. */
+int ia2c_mlp_forward(const float* params, const float* x, float* y, float* h1_out, int64_t rows, int32_t F, int32_t O,
                      int32_t nets, int32_t softmax, void* stream);
 
 /* Backward of the above for ONE net: given dy float[rows,O] = dL/d(output) (for softmax nets dL/dprobs),
  * accumulates dL/dparams into grad float[P] (grad += if accumulate != 0, else overwritten) and, if dx
  * is not NULL, writes dL/dx float[rows,F].  Replaces autograd through ac_nets.py:34-41.
+ *   h1_saved float[rows,6] (may be NULL): ia2c_mlp_forward's h1_out for the same x and params;
  *   workspace float[ia2c_mlp_backward_workspace(rows,F,O)] */
 size_t ia2c_mlp_backward_workspace(int64_t rows, int32_t F, int32_t O);
-int ia2c_mlp_backward(const float* params, const float* x, const float* dy, float* grad, float* dx,
+int ia2c_mlp_backward(const float* params, const float* x, const float* dy, const float* h1_saved, float* grad, float* dx,
                       float* workspace, int64_t rows, int32_t F, int32_t O, int32_t softmax,
                       int32_t accumulate, void* stream);
 

@@ -97,7 +97,8 @@ def test_unmodified_reference_scripts_resolve_against_the_drop_in_modules(script
         pytest.skip("CUDA present: the scripts would train for hours")
     env = dict(os.environ)
     env["PYTHONPATH"] = os.pathsep.join([ROOT, os.path.join(ROOT, "ia2c_b200", "compat"), os.path.join(ROOT, "ia2c_b200", "compat_gym")])
-    r = subprocess.run([sys.executable, os.path.join(ref, script)], capture_output=True, text=True, env=env, cwd="/tmp", timeout=300)
+    # -P: do not put the script's own directory (which holds the reference modules) in front of PYTHONPATH
+    r = subprocess.run([sys.executable, "-P", os.path.join(ref, script)], capture_output=True, text=True, env=env, cwd="/tmp", timeout=300)
     assert r.returncode != 0
     assert "no CPU fallback" in r.stderr, r.stderr[-2000:]
     assert "ModuleNotFoundError" not in r.stderr and "ImportError" not in r.stderr

@@ -122,7 +122,6 @@ def test_ia2c_flow_through_compat_modules_and_vector_env(golden):
         obs = torch.zeros(T, E, 6); nobs = torch.zeros(T, E, 6); rew = torch.zeros(T, E)
         ta = torch.zeros(T, E, 2); pa = torch.zeros(T, E, 2); tna = torch.zeros(T, E, 2); pna = torch.zeros(T, E, 2)
         s, _ = envs.reset()
-        s = np.asarray(s.cpu() if hasattr(s, "cpu") else s)
         assert np.array_equal(s, g["env/reset_obs"][ep])
         a = [actors[k].sample_action(torch.tensor(s), grad=True) for k in range(2)]
         pred = [None, None]

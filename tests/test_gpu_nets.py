@@ -62,13 +62,13 @@ def test_mlp_forward_backward_vs_oracle(rows, F, O, softmax):
         x = np.eye(F, dtype=np.float32)[rng.randint(0, F, rows)]
     dy = rng.randn(rows, O).astype(np.float32)
     y = torch.empty(rows, O, device="cuda")
-    _lib.check(lib.ia2c_mlp_forward(dptr((flat)), dptr((x)), _lib.ptr(y), rows, F, O, 1, softmax, _lib.stream_ptr()))
+    _lib.check(lib.ia2c_mlp_forward(dptr((flat)), dptr((x)), _lib.ptr(y), None, rows, F, O, 1, softmax, _lib.stream_ptr()))
     ref, cache = NN.forward(flat.astype(np.float64), x, F, O, softmax=bool(softmax), keep=True)
     assert rel_err(host(y), ref) < RTOL
     grad = torch.full((flat.size,), 7.0, device="cuda")
     dx = torch.empty(rows, F, device="cuda")
     ws = torch.empty(lib.ia2c_mlp_backward_workspace(rows, F, O), device="cuda")
-    _lib.check(lib.ia2c_mlp_backward(dptr((flat)), dptr((x)), dptr((dy)), _lib.ptr(grad), _lib.ptr(dx), _lib.ptr(ws),
+    _lib.check(lib.ia2c_mlp_backward(dptr((flat)), dptr((x)), dptr((dy)), None, _lib.ptr(grad), _lib.ptr(dx), _lib.ptr(ws),
                                      rows, F, O, softmax, 0, _lib.stream_ptr()))
     dyp = dy.astype(np.float64)
     if softmax:
@@ -78,8 +78,10 @@ def test_mlp_forward_backward_vs_oracle(rows, F, O, softmax):
     W1 = flat[:6 * F].reshape(6, F).astype(np.float64)
     dz1 = ((dyp @ NN.unpack(flat.astype(np.float64), F, O)[4]) * (cache[4] > 0)) @ NN.unpack(flat.astype(np.float64), F, O)[2] * (cache[2] > 0)
     assert rel_err(host(dx), dz1 @ W1) < RTOL
-    # accumulate mode adds onto the existing gradient
-    _lib.check(lib.ia2c_mlp_backward(dptr((flat)), dptr((x)), dptr((dy)), _lib.ptr(grad), None, _lib.ptr(ws),
+    # accumulate mode adds onto the existing gradient; this time with the layer-1 activations saved by the forward
+    h1s = torch.empty(rows, 6, device="cuda")
+    _lib.check(lib.ia2c_mlp_forward(dptr((flat)), dptr((x)), _lib.ptr(y), _lib.ptr(h1s), rows, F, O, 1, softmax, _lib.stream_ptr()))
+    _lib.check(lib.ia2c_mlp_backward(dptr((flat)), dptr((x)), dptr((dy)), _lib.ptr(h1s), _lib.ptr(grad), None, _lib.ptr(ws),
                                      rows, F, O, softmax, 1, _lib.stream_ptr()))
     assert rel_err(host(grad), 2 * gref) < RTOL
 
@@ -93,7 +95,7 @@ def test_multi_net_forward():
     flat = (rng.randn(nets, 105) * 0.5).astype(np.float32)
     x = rng.randn(rows, 6).astype(np.float32)
     y = torch.empty(nets, rows, 3, device="cuda")
-    _lib.check(lib.ia2c_mlp_forward(dptr((flat)), dptr((x)), _lib.ptr(y), rows, 6, 3, nets, 1, _lib.stream_ptr()))
+    _lib.check(lib.ia2c_mlp_forward(dptr((flat)), dptr((x)), _lib.ptr(y), None, rows, 6, 3, nets, 1, _lib.stream_ptr()))
     for n in range(nets):
         assert rel_err(host(y)[n], NN.forward(flat[n].astype(np.float64), x, 6, 3, softmax=True)) < RTOL
 
