@@ -15,6 +15,8 @@
 //            (lossless), 8 B per (env, agent, modelled other); likelihood synthesised from the other
 //            agent's action; stages the models, actions and a k/100 table in shared memory and
 //            reduces the predicted actions per agent (mode) with shared-memory counters.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace ia2c {
@@ -232,8 +234,150 @@ __global__ void debug_divide_kernel(const double* __restrict__ a, const double* 
     q_ieee[i] = __ddiv_rn(a[i], b[i]);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Table-driven pairwise update for many modelled others (K >= 32).
+//
+// belief_pairs_kernel is bound by the fp64 pipe (~100 DP instructions per record against 16 B of traffic).  Two
+// observations remove two thirds of them without changing a single output bit:
+//  (1) the un-normalised posterior bp[m] = (l0*(F[m][0]*p) + l1*(F[m][1]*p)) + l2*(F[m][2]*p) depends only on the
+//      agent's model m, the SEEN action (3 likelihood rows) and the prior, which is k/100 with integer k in 0..100.
+//      A block that owns ONE agent therefore tabulates all 3*M*101 values once (same fp64 operations, same
+//      order) and each record needs M table lookups instead of 6M multiply/adds;
+//  (2) the mixture prediction is only COMPARED with u.  It is evaluated in fp32 (a different pipe); when u lies
+//      within 1e-5 of a decision boundary — the fp32 error is below 1e-6 — the record falls back to the exact
+//      fp64 sequence.  The fallback rate is ~6e-5 per record.
+// Per record that leaves S, one shared reciprocal, M corrected divisions and M roundings on the fp64 pipe.
+// Block = (agent i, chunk of envs): the agent's K records of one env are 8*K contiguous bytes.
+template <int M>
+__global__ void __launch_bounds__(kThreads) belief_pairs_table_kernel(PairsArgs P) {
+    constexpr int A = IA2C_AGENT_ACTIONS;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int N = P.N, K = P.K, i = blockIdx.y;
+    const int EC = P.envs_per_block;
+    const int64_t e0 = (int64_t)blockIdx.x * EC;
+    const int n_envs = (int)min((int64_t)EC, P.E - e0);
+    double* tab = reinterpret_cast<double*>(smem_raw);              // [104]   k/100
+    double* bpt = tab + 104;                                        // [A][M][101]
+    double* fa = bpt + A * M * 101;                                 // [M][A]
+    float* fa32 = reinterpret_cast<float*>(fa + M * A);             // [M][A]
+    int* counts = reinterpret_cast<int*>(fa32 + ((M * A + 3) & ~3)); // [EC][A]
+    uint8_t* act = reinterpret_cast<uint8_t*>(counts + EC * A);     // [EC][N]
+    for (int k = threadIdx.x; k <= 100; k += blockDim.x) tab[k] = __ddiv_rn((double)k, 100.0);
+    for (int k = threadIdx.x; k < M * A; k += blockDim.x) {
+        fa[k] = P.filter_action[(int64_t)i * M * A + k];
+        fa32[k] = (float)fa[k];
+    }
+    for (int k = threadIdx.x; k < n_envs * A; k += blockDim.x) counts[k] = 0;
+    for (int k = threadIdx.x; k < n_envs * N; k += blockDim.x) act[k] = P.actions[e0 * N + k];
+    __syncthreads();
+    for (int x = threadIdx.x; x < A * M * 101; x += blockDim.x) {
+        const int seen = x / (M * 101), m = (x / 101) % M, k = x % 101;
+        const double p = tab[k];
+        double acc = __dmul_rn(seen == 0 ? 0.8 : 0.1, __dmul_rn(fa[m * A + 0], p));
+#pragma unroll
+        for (int a = 1; a < A; ++a) acc = __dadd_rn(acc, __dmul_rn(seen == a ? 0.8 : 0.1, __dmul_rn(fa[m * A + a], p)));
+        bpt[x] = acc;
+    }
+    __syncthreads();
+    const int prior_k = (int)rint(100.0 / M);
+    const int total = n_envs * K;
+    for (int q = threadIdx.x; q < total; q += blockDim.x) {
+        const int el = q / K, jj = q - el * K;
+        const int j = jj + (jj >= i);
+        const int64_t e = e0 + el;
+        const int64_t rec = (e * N + i) * (int64_t)K + jj;
+        uint2 raw = make_uint2(0u, 0u);
+        if (!P.reset_prior) raw = *reinterpret_cast<const uint2*>(P.records + rec * IA2C_BELIEF_RECORD);
+        const double* row = bpt + act[el * N + j] * (M * 101);
+        double bp[M], b[M];
+#pragma unroll
+        for (int m = 0; m < M; ++m) {
+            const uint32_t word = m < 4 ? raw.x : raw.y;
+            const int k = P.reset_prior ? prior_k : (int)((word >> (8 * (m & 3))) & 0xFFu);
+            bp[m] = row[m * 101 + k];
+        }
+        double S = bp[0];
+#pragma unroll
+        for (int m = 1; m < M; ++m) S = __dadd_rn(S, bp[m]);
+        const double rS = drcp_seq(S);
+        uint32_t lo = 0, hi = 0;
+        float bf[M];
+#pragma unroll
+        for (int m = 0; m < M; ++m) {
+            b[m] = ddiv_with(bp[m], S, rS);
+            bf[m] = (float)b[m];
+            const uint32_t k = (uint32_t)__double2int_rn(__dmul_rn(b[m], 100.0));
+            if (m < 4) lo |= k << (8 * m); else hi |= k << (8 * (m - 4));
+            if (P.belief_out) P.belief_out[rec * M + m] = (uint8_t)k;
+        }
+        const double u = P.u_injected ? P.u_injected[rec]
+                                      : philox_uniform_f64(P.seed, kStreamBelief, P.episode, P.t,
+                                                           (uint64_t)(((P.env_offset + e) * N + i) * (int64_t)K + jj));
+        // fp32 screening of the inverse-CDF decision
+        float pf[A];
+#pragma unroll
+        for (int a = 0; a < A; ++a) {
+            float acc = 0.f;
+#pragma unroll
+            for (int m = 0; m < M; ++m) acc = fmaf(bf[m], fa32[m * A + a], acc);
+            pf[a] = acc;
+        }
+        const float uf = (float)u;
+        float cf = pf[0];
+        int ap = 0;
+        bool found = uf < cf, risky = fabsf(uf - cf) < 1e-5f;
+#pragma unroll
+        for (int a = 1; a < A; ++a) {
+            cf += pf[a];
+            risky |= fabsf(uf - cf) < 1e-5f;
+            if (!found && uf < cf) { ap = a; found = true; }
+        }
+        if (risky) {   // exact sequence, identical to belief_core
+            double c = 0.0;
+            ap = 0;
+            found = false;
+#pragma unroll
+            for (int a = 0; a < A; ++a) {
+                double acc = 0.0;
+#pragma unroll
+                for (int m = 0; m < M; ++m) acc = __dadd_rn(acc, __dmul_rn(b[m], fa[m * A + a]));
+                c = (a == 0) ? acc : __dadd_rn(c, acc);
+                if (!found && u < c) { ap = a; found = true; }
+            }
+        }
+        hi |= (uint32_t)ap << 16;  // byte 6
+        *reinterpret_cast<uint2*>(P.records + rec * IA2C_BELIEF_RECORD) = make_uint2(lo, hi);
+        if (P.pred_out) P.pred_out[rec] = (uint8_t)ap;
+        if (P.pred_partner_out) atomicAdd(&counts[el * A + ap], 1);   // ptxas aggregates same-address lanes (REDUX)
+    }
+    if (P.pred_partner_out) {
+        __syncthreads();
+        for (int el = threadIdx.x; el < n_envs; el += blockDim.x) {
+            const int* c = counts + el * A;
+            int best = 0;
+#pragma unroll
+            for (int a = 1; a < A; ++a) best = c[a] > c[best] ? a : best;   // ties -> lowest action
+            P.pred_partner_out[(e0 + el) * N + i] = (uint8_t)best;
+        }
+    }
+}
+
+template <int M>
+int launch_pairs_table(PairsArgs& P, cudaStream_t stream) {
+    P.envs_per_block = std::max(1, std::min(64, 4096 / P.K));
+    const int64_t env_blocks = (P.E + P.envs_per_block - 1) / P.envs_per_block;
+    size_t smem = (104 + 3 * M * 101 + M * 3) * sizeof(double) + ((M * 3 + 3) & ~3) * sizeof(float) +
+                  (size_t)P.envs_per_block * 3 * sizeof(int) + (size_t)P.envs_per_block * P.N;
+    smem = (smem + 15) & ~size_t(15);
+    if (smem > 48 * 1024) cudaFuncSetAttribute(belief_pairs_table_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    dim3 grid((unsigned)env_blocks, P.N);
+    belief_pairs_table_kernel<M><<<grid, kThreads, smem, stream>>>(P);
+    return check_launch("belief_pairs_table_kernel");
+}
+
 template <int M>
 int launch_pairs(PairsArgs& P, cudaStream_t stream) {
+    if (P.K >= 32 && P.N <= 65535) return launch_pairs_table<M>(P, stream);
     const int64_t per_env = (int64_t)P.N * P.K;
     const int target = 4096;  // records per block
     if (per_env <= target) {
