@@ -324,10 +324,10 @@ def run_ours(args):
     # ---- e2e: the public host-buffer call — pinned uniforms H2D, episode, losses + returns D2H, sync
     n_bufs = 4
     rng = np.random.RandomState(rank)
-    ua = [torch.from_numpy(rng.rand(T + 1, E_gpu, N).astype(np.float32)).pin_memory() for _ in range(n_bufs)]
-    ub = [torch.from_numpy(rng.rand(T + 1, E_gpu, N, N - 1)).pin_memory() for _ in range(n_bufs)]
-    h2d = ua[0].numel() * 4 + ub[0].numel() * 8
-    d2h = 2 * N * 4 + E_gpu * 8
+    tapes = [tr.pack_host_tape(rng.rand(T + 1, E_gpu, N).astype(np.float32), rng.rand(T + 1, E_gpu, N, N - 1))
+             for _ in range(n_bufs)]
+    h2d = tapes[0].numel()
+    d2h = tr._result_region.numel()
 
     chunk = 50   # episodes per pipelined host call (each call ends with one stream sync)
 
@@ -335,7 +335,7 @@ def run_ours(args):
         done = 0
         while done < n:
             m = min(chunk, n - done)
-            tr.train_episodes_host([ua[(done + j) % n_bufs] for j in range(m)], [ub[(done + j) % n_bufs] for j in range(m)])
+            tr.train_episodes_host([tapes[(done + j) % n_bufs] for j in range(m)])
             done += m
 
     e2e_run(3)
@@ -380,7 +380,8 @@ def run_ours(args):
         "e2e": {"value": units * K / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms / K, "wall_ms_per_step": e2e_wall_ms / K,
                 "api": ("IA2CTrainer.train_episodes_host -> ia2c_train_episodes_host (C ABI, pinned host tapes in, losses + returns "
-                        "out per episode; H2D of episode k+1 overlaps episode k; one sync per 50 episodes)") if world == 1 else
+                        "out per episode; one H2D and one D2H copy per episode, H2D of episode k+1 overlaps episode k; one sync per "
+                        "50 episodes)") if world == 1 else
                        "IA2CTrainer.train_episodes_host (torch copy stream + per-phase C-ABI calls + NCCL all-reduce)"},
         "gpu_launches": int(launches),
         "roofline": {"kernel": kname, "bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,

@@ -84,7 +84,9 @@ SIGNATURES = {
     "ia2c_train_episode": (C.c_int, [_DP, vp]),
     "ia2c_train_episode_host": (C.c_int, [_DP, vp, vp, vp, vp, vp]),
     "ia2c_train_episode_timed": (C.c_int, [_DP, vp, vp]),
-    "ia2c_train_episodes_host": (C.c_int, [_DP, vp, vp, i32, C.POINTER(vp), C.POINTER(vp), vp, vp, vp]),
+    "ia2c_host_tape_bytes": (C.c_size_t, [_DP]),
+    "ia2c_host_result_bytes": (C.c_size_t, [_DP]),
+    "ia2c_train_episodes_host": (C.c_int, [_DP, vp, i32, C.POINTER(vp), vp, vp]),
 }
 
 _lib = None

@@ -714,20 +714,34 @@ int pipe_init() {
 }
 }  // namespace
 
-extern "C" int ia2c_train_episodes_host(const ia2c_episode_desc* d, float* stage_b_u_action, double* stage_b_u_belief,
-                                        int32_t n_episodes, const float* const* host_u_action,
-                                        const double* const* host_u_belief, float* host_loss_out,
-                                        double* host_ep_return, void* stream) {
+static inline size_t align8(size_t x) { return (x + 7) & ~size_t(7); }
+
+extern "C" size_t ia2c_host_tape_bytes(const ia2c_episode_desc* d) {
+    if (!d) return 0;
+    const size_t n_act = (size_t)(d->T + 1) * d->E * d->N;
+    return align8(n_act * sizeof(float)) + n_act * (d->N - 1) * sizeof(double);
+}
+extern "C" size_t ia2c_host_result_bytes(const ia2c_episode_desc* d) {
+    if (!d) return 0;
+    return align8(2 * (size_t)d->N * sizeof(float)) + (size_t)d->E * sizeof(double);
+}
+
+extern "C" int ia2c_train_episodes_host(const ia2c_episode_desc* d, void* stage_b, int32_t n_episodes,
+                                        const void* const* host_tapes, void* host_results, void* stream) {
     if (int rc = validate(d, "ia2c_train_episodes_host")) return rc;
     IA2C_REQUIRE(!(d->flags & IA2C_FLAG_SKIP_ADAM), "ia2c_train_episodes_host: single-rank entry point (SKIP_ADAM set)");
-    IA2C_REQUIRE(n_episodes > 0 && host_u_action && host_u_belief && host_loss_out && host_ep_return, "ia2c_train_episodes_host: null host pointer or n_episodes=%d", n_episodes);
-    IA2C_REQUIRE(d->inj_u_action && d->inj_u_belief && stage_b_u_action && stage_b_u_belief, "ia2c_train_episodes_host: two device staging sets are required");
+    IA2C_REQUIRE(n_episodes > 0 && host_tapes && host_results, "ia2c_train_episodes_host: null host pointer or n_episodes=%d", n_episodes);
+    const size_t n_act = (size_t)(d->T + 1) * d->E * d->N;
+    const size_t off_b = align8(n_act * sizeof(float)), tape_bytes = ia2c_host_tape_bytes(d);
+    const size_t off_ret = align8(2 * (size_t)d->N * sizeof(float)), res_bytes = ia2c_host_result_bytes(d);
+    // ONE copy per direction per episode: the two uniform tapes share a staging region, losses and returns a result region
+    IA2C_REQUIRE(d->inj_u_action && stage_b && (const char*)d->inj_u_belief == (const char*)d->inj_u_action + off_b,
+                 "ia2c_train_episodes_host: inj_u_belief must follow inj_u_action in one staging region (ia2c_host_tape_bytes)");
+    IA2C_REQUIRE((const char*)d->ep_return == (const char*)d->loss_out + off_ret,
+                 "ia2c_train_episodes_host: ep_return must follow loss_out in one result region (ia2c_host_result_bytes)");
     if (int rc = pipe_init()) return rc;
     cudaStream_t s = as_stream(stream);
-    const size_t n_act = (size_t)(d->T + 1) * d->E * d->N;
-    const size_t b_act = n_act * sizeof(float), b_bel = n_act * (d->N - 1) * sizeof(double);
-    float* st_a[2] = {const_cast<float*>(d->inj_u_action), stage_b_u_action};
-    double* st_b[2] = {const_cast<double*>(d->inj_u_belief), stage_b_u_belief};
+    char* stage[2] = {reinterpret_cast<char*>(const_cast<float*>(d->inj_u_action)), reinterpret_cast<char*>(stage_b)};
     // the copy stream must not overwrite a staging set that earlier work on `s` may still read
     if (cudaEventRecord(g_pipe.consumed[0], s) != cudaSuccess || cudaEventRecord(g_pipe.consumed[1], s) != cudaSuccess)
         return check_launch("cudaEventRecord");
@@ -735,18 +749,16 @@ extern "C" int ia2c_train_episodes_host(const ia2c_episode_desc* d, float* stage
     for (int k = 0; k < n_episodes; ++k) {
         const int b = k & 1;
         cudaStreamWaitEvent(g_pipe.copy, g_pipe.consumed[b], 0);
-        if (cudaMemcpyAsync(st_a[b], host_u_action[k], b_act, cudaMemcpyHostToDevice, g_pipe.copy) != cudaSuccess ||
-            cudaMemcpyAsync(st_b[b], host_u_belief[k], b_bel, cudaMemcpyHostToDevice, g_pipe.copy) != cudaSuccess)
+        if (cudaMemcpyAsync(stage[b], host_tapes[k], tape_bytes, cudaMemcpyHostToDevice, g_pipe.copy) != cudaSuccess)
             return check_launch("memcpy H2D uniforms");
         cudaEventRecord(g_pipe.copied[b], g_pipe.copy);
         cudaStreamWaitEvent(s, g_pipe.copied[b], 0);
-        e.inj_u_action = st_a[b];
-        e.inj_u_belief = st_b[b];
+        e.inj_u_action = reinterpret_cast<const float*>(stage[b]);
+        e.inj_u_belief = reinterpret_cast<const double*>(stage[b] + off_b);
         e.episode = d->episode + (uint32_t)k;
         if (int rc = ia2c_train_episode(&e, stream)) return rc;
         cudaEventRecord(g_pipe.consumed[b], s);
-        if (cudaMemcpyAsync(host_loss_out + (size_t)k * 2 * d->N, d->loss_out, 2 * (size_t)d->N * sizeof(float), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
-            cudaMemcpyAsync(host_ep_return + (size_t)k * d->E, d->ep_return, (size_t)d->E * sizeof(double), cudaMemcpyDeviceToHost, s) != cudaSuccess)
+        if (cudaMemcpyAsync(reinterpret_cast<char*>(host_results) + (size_t)k * res_bytes, d->loss_out, res_bytes, cudaMemcpyDeviceToHost, s) != cudaSuccess)
             return check_launch("memcpy D2H results");
     }
     if (cudaStreamSynchronize(s) != cudaSuccess) return check_launch("stream sync");

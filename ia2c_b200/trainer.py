@@ -74,11 +74,14 @@ class IA2CTrainer:
         self.actor_m, self.actor_v = z((N, _lib.ACTOR_P), f32), z((N, _lib.ACTOR_P), f32)
         self.critic_m, self.critic_v = z((N, _lib.CRITIC_P), f32), z((N, _lib.CRITIC_P), f32)
         self.actor_step, self.critic_step = z((N,), i32), z((N,), i32)
-        self.loss_out = z((2, N), f32)
+        # losses and episode returns share one "result region" so that one D2H copy returns both
+        self._off_ret = (2 * N * 4 + 7) & ~7
+        self._result_region = z((self._off_ret + E * 8,), u8)
+        self.loss_out = self._result_region[:2 * N * 4].view(f32).view(2, N)
         self.filter_action = z((N, M, N_ACTIONS), f64)
         self.env_state, self.env_hist = z((E,), i32), z((E,), f64)
         self.env_cls, self.env_elapsed = z((E, 2), u8), z((E,), i32)
-        self.ep_return = z((E,), f64)
+        self.ep_return = self._result_region[self._off_ret:].view(f64)
         self.obs, self.reward = z((T + 1, E, N_FEATURES), f32), z((T, E), f32)
         self.act, self.partner_true, self.partner_pred = z((T + 1, E, N), u8), z((T + 1, E, N), u8), z((T + 1, E, N), u8)
         self.belief_records = z((E, N, K, _lib.BELIEF_RECORD), u8)
@@ -180,8 +183,13 @@ class IA2CTrainer:
             return t
 
         self.inj_actions = put(actions, torch.uint8, (T + 1, E, N))
-        self.inj_u_action = put(u_action, torch.float32, (T + 1, E, N))
-        self.inj_u_belief = put(u_belief, torch.float64, (T + 1, E, N, K))
+        if u_action is not None and u_belief is not None:   # both tapes: keep them in staging region A (one region)
+            self._ensure_stage()
+            self.inj_u_action.copy_(put(u_action, torch.float32, (T + 1, E, N)))
+            self.inj_u_belief.copy_(put(u_belief, torch.float64, (T + 1, E, N, K)))
+        else:
+            self.inj_u_action = put(u_action, torch.float32, (T + 1, E, N))
+            self.inj_u_belief = put(u_belief, torch.float64, (T + 1, E, N, K))
         self.desc.inj_actions = self.inj_actions.data_ptr() if self.inj_actions is not None else None
         self.desc.inj_u_action = self.inj_u_action.data_ptr() if self.inj_u_action is not None else None
         self.desc.inj_u_belief = self.inj_u_belief.data_ptr() if self.inj_u_belief is not None else None
@@ -245,78 +253,89 @@ class IA2CTrainer:
         self.episode += 1
         return self._record_stats()
 
-    def train_episodes_host(self, host_u_action, host_u_belief):
-        """Pipelined end-to-end form: lists of per-episode pinned host tapes in, per-episode losses and returns
-        out.  The H2D copy of episode k+1 overlaps episode k (``ia2c_train_episodes_host``); single rank."""
-        n = len(host_u_action)
+    # ---- host-tape pipeline (end-to-end form) -----------------------------------------------------------------
+    def host_tape_bytes(self):
+        n_act = (self.T + 1) * self.E * self.N
+        return ((n_act * 4 + 7) & ~7) + n_act * self.K * 8
+
+    def pack_host_tape(self, u_action, u_belief):
+        """One pinned host buffer per episode: [u_action f32[T+1,E,N] | pad | u_belief f64[T+1,E,N,K]]."""
+        n_act = (self.T + 1) * self.E * self.N
+        off = (n_act * 4 + 7) & ~7
+        tape = torch.empty(self.host_tape_bytes(), dtype=torch.uint8).pin_memory()
+        tape[:n_act * 4].view(torch.float32).copy_(torch.as_tensor(np.asarray(u_action), dtype=torch.float32).reshape(-1))
+        tape[off:].view(torch.float64).copy_(torch.as_tensor(np.asarray(u_belief), dtype=torch.float64).reshape(-1))
+        return tape
+
+    def _ensure_stage(self):
+        """Two device staging regions for the tapes; the desc's injected-uniform pointers are views of region A."""
+        if getattr(self, "_stage", None) is None:
+            nbytes = self.host_tape_bytes()
+            self._stage = [torch.empty(nbytes, dtype=torch.uint8, device=self.device) for _ in range(2)]
+        self._point_at_stage(0)
+
+    def _point_at_stage(self, b):
         T, E, N, K = self.T, self.E, self.N, self.K
+        n_act = (T + 1) * E * N
+        off = (n_act * 4 + 7) & ~7
+        self.inj_u_action = self._stage[b][:n_act * 4].view(torch.float32).view(T + 1, E, N)
+        self.inj_u_belief = self._stage[b][off:].view(torch.float64).view(T + 1, E, N, K)
+        self.desc.inj_u_action, self.desc.inj_u_belief = self.inj_u_action.data_ptr(), self.inj_u_belief.data_ptr()
+
+    def train_episodes_host(self, host_tapes):
+        """Pipelined end-to-end form: a list of per-episode pinned host tapes (``pack_host_tape``) in, per-episode
+        losses and returns out.  One H2D copy per episode, overlapping the previous episode's compute, and one D2H
+        copy of the result region (``ia2c_train_episodes_host``; multi-rank: the same pipeline with torch streams)."""
+        n = len(host_tapes)
+        N, E = self.N, self.E
+        self._ensure_stage()
+        res_bytes = self._result_region.numel()
+        if getattr(self, "_h_results", None) is None or self._h_results.shape[0] < n:
+            self._h_results = torch.zeros(n, res_bytes, dtype=torch.uint8).pin_memory()
         if self.world > 1:
-            return self._train_episodes_host_multirank(host_u_action, host_u_belief)
-        if self.inj_u_action is None or self.inj_u_belief is None:
-            self.inject(u_action=torch.zeros(T + 1, E, N), u_belief=torch.zeros(T + 1, E, N, K, dtype=torch.float64))
-        if getattr(self, "_stage_b", None) is None:
-            self._stage_b = (torch.empty_like(self.inj_u_action), torch.empty_like(self.inj_u_belief))
-        if getattr(self, "_h_multi", None) is None or self._h_multi[0].shape[0] < n:
-            self._h_multi = (torch.zeros(n, 2, N, dtype=torch.float32).pin_memory(),
-                             torch.zeros(n, E, dtype=torch.float64).pin_memory())
-        pa = (C.c_void_p * n)(*[t.data_ptr() for t in host_u_action])
-        pb = (C.c_void_p * n)(*[t.data_ptr() for t in host_u_belief])
-        self.desc.episode = self.episode
-        with torch.cuda.device(self.device):
-            _lib.check(self.lib.ia2c_train_episodes_host(
-                C.byref(self.desc), self._stage_b[0].data_ptr(), self._stage_b[1].data_ptr(), n, pa, pb,
-                self._h_multi[0].data_ptr(), self._h_multi[1].data_ptr(), self._stream()), "ia2c_train_episodes_host")
-        self.episode += n
+            self._pipeline_multirank(host_tapes)
+        else:
+            ptrs = (C.c_void_p * n)(*[t.data_ptr() for t in host_tapes])
+            self.desc.episode = self.episode
+            with torch.cuda.device(self.device):
+                _lib.check(self.lib.ia2c_train_episodes_host(C.byref(self.desc), self._stage[1].data_ptr(), n, ptrs,
+                                                             self._h_results.data_ptr(), self._stream()),
+                           "ia2c_train_episodes_host")
+            self.episode += n
         out = []
         for k in range(n):
-            self._h_loss.copy_(self._h_multi[0][k])
-            self._h_return.copy_(self._h_multi[1][k])
-            out.append(self._record_stats())
+            row = self._h_results[k]
+            self._h_loss.copy_(row[:2 * N * 4].view(torch.float32).view(2, N))
+            self._h_return.copy_(row[self._off_ret:].view(torch.float64))
+            out.append(self._record_stats(windows=(k == n - 1)))   # window means once per call, like ia2c.py's print cadence
         return out
 
-    def _train_episodes_host_multirank(self, host_u_action, host_u_belief):
-        """Same pipeline with torch streams/events around the per-phase entry points (the NCCL all-reduces sit
+    def _pipeline_multirank(self, host_tapes):
+        """Same pipeline with torch streams/events around the per-phase entry points (the gradient exchanges sit
         between them, so the single C call cannot be used)."""
-        n = len(host_u_action)
-        T, E, N, K = self.T, self.E, self.N, self.K
-        if self.inj_u_action is None or self.inj_u_belief is None:
-            self.inject(u_action=torch.zeros(T + 1, E, N), u_belief=torch.zeros(T + 1, E, N, K, dtype=torch.float64))
-        if getattr(self, "_stage_b", None) is None:
-            self._stage_b = (torch.empty_like(self.inj_u_action), torch.empty_like(self.inj_u_belief))
-        if getattr(self, "_h_multi", None) is None or self._h_multi[0].shape[0] < n:
-            self._h_multi = (torch.zeros(n, 2, N, dtype=torch.float32).pin_memory(),
-                             torch.zeros(n, E, dtype=torch.float64).pin_memory())
         if getattr(self, "_copy_stream", None) is None:
             self._copy_stream = torch.cuda.Stream(device=self.device)
-        stage = [(self.inj_u_action, self.inj_u_belief), self._stage_b]
         cur = torch.cuda.current_stream(self.device)
         copied = [torch.cuda.Event(), torch.cuda.Event()]
         consumed = [torch.cuda.Event(), torch.cuda.Event()]
         for ev_ in consumed:
             ev_.record(cur)
-        for k in range(n):
+        for k, tape in enumerate(host_tapes):
             b = k & 1
             with torch.cuda.stream(self._copy_stream):
                 self._copy_stream.wait_event(consumed[b])
-                stage[b][0].copy_(host_u_action[k], non_blocking=True)
-                stage[b][1].copy_(host_u_belief[k], non_blocking=True)
+                self._stage[b].copy_(tape, non_blocking=True)
                 copied[b].record(self._copy_stream)
             cur.wait_event(copied[b])
-            self.desc.inj_u_action, self.desc.inj_u_belief = stage[b][0].data_ptr(), stage[b][1].data_ptr()
+            self._point_at_stage(b)
             self.rollout()
             self.update()
             consumed[b].record(cur)
             self.episode += 1
-            self._h_multi[0][k].copy_(self.loss_out, non_blocking=True)
-            self._h_multi[1][k].copy_(self.ep_return, non_blocking=True)
+            self._h_results[k].copy_(self._result_region, non_blocking=True)
         cur.synchronize()
-        self.desc.inj_u_action, self.desc.inj_u_belief = self.inj_u_action.data_ptr(), self.inj_u_belief.data_ptr()
-        out = []
-        for k in range(n):
-            self._h_loss.copy_(self._h_multi[0][k])
-            self._h_return.copy_(self._h_multi[1][k])
-            out.append(self._record_stats())
-        return out
+        self._point_at_stage(0)
+        self.check_comm()
 
     def train_episode_timed(self):
         """One episode with CUDA events between the kernels (profiling): returns the five warm durations in ms
@@ -342,16 +361,24 @@ class IA2CTrainer:
         torch.cuda.current_stream(self.device).synchronize()
         return self._record_stats()
 
-    def _record_stats(self):
+    def _record_stats(self, windows=True):
+        """Append this episode's losses / returns to the reference's windows (20-deep loss windows, ac_nets.py:77-80;
+        last-50 returns, ia2c.py:134).  The window means are what ia2c.py prints every 10 episodes; computing them is
+        host work proportional to 50*E, so the pipelined path asks for them only when it needs them."""
         loss = self._h_loss.numpy().copy()
         ret = self._h_return.numpy().copy()
         self.critic_losses.append(loss[0]), self.actor_losses.append(loss[1])
-        del self.critic_losses[:-20], self.actor_losses[:-20]      # 20-deep loss windows (ac_nets.py:77-80)
+        del self.critic_losses[:-20], self.actor_losses[:-20]
         self.reward_lst.append(ret)
-        del self.reward_lst[:-50]                                  # mean of the last 50 (ia2c.py:134)
-        return dict(critic_loss=loss[0], actor_loss=loss[1], ep_return=ret,
-                    critic_loss_window=np.mean(self.critic_losses, axis=0),
-                    actor_loss_window=np.mean(self.actor_losses, axis=0), mean_return=np.mean(self.reward_lst))
+        del self.reward_lst[:-50]
+        out = dict(critic_loss=loss[0], actor_loss=loss[1], ep_return=ret)
+        if windows:
+            out.update(self.window_stats())
+        return out
+
+    def window_stats(self):
+        return dict(critic_loss_window=np.mean(self.critic_losses, axis=0), actor_loss_window=np.mean(self.actor_losses, axis=0),
+                    mean_return=np.mean(self.reward_lst))
 
     # ------------------------------------------------------------------ checkpoint / resume (SURVEY.md §8 f4)
     _CKPT_TENSORS = ("actor_params", "critic_params", "actor_grad_accum", "actor_m", "actor_v", "critic_m", "critic_v",

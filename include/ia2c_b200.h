@@ -260,15 +260,17 @@ int ia2c_train_episode_host(const ia2c_episode_desc* d, const float* host_u_acti
  * reduce+Adam} in milliseconds. */
 int ia2c_train_episode_timed(const ia2c_episode_desc* d, float* host_ms_out, void* stream);
 
-/* Pipelined form of the above for n_episodes consecutive episodes: host_u_action[k] / host_u_belief[k] are
- * the (pinned) host tapes of episode k; the H2D copy of episode k+1 overlaps the compute of episode k on an
- * internal copy stream (two device staging sets: desc.inj_u_* and stage_b_*); every episode's losses
- * (host_loss_out float[n,2,N]) and returns (host_ep_return double[n,E]) are read back; one sync at the end.
+/* Pipelined form of the above for n_episodes consecutive episodes, ONE copy per direction per episode:
+ *   host_tapes[k]  (pinned) = [u_action float[T+1,E,N] | pad to 8 B | u_belief double[T+1,E,N,K]], ia2c_host_tape_bytes;
+ *   host_results   (pinned) = n_episodes x [loss float[2,N] | pad to 8 B | ep_return double[E]], ia2c_host_result_bytes.
+ * On the device the two tapes share one staging region (desc.inj_u_belief must follow desc.inj_u_action at the padded
+ * offset; stage_b is a second region of the same size) and desc.ep_return follows desc.loss_out the same way.  The H2D
+ * copy of episode k+1 overlaps the compute of episode k on an internal copy stream; one host sync at the end.
  * Episode numbers are desc.episode .. desc.episode + n_episodes - 1. */
-int ia2c_train_episodes_host(const ia2c_episode_desc* d, float* stage_b_u_action, double* stage_b_u_belief,
-                             int32_t n_episodes, const float* const* host_u_action,
-                             const double* const* host_u_belief, float* host_loss_out, double* host_ep_return,
-                             void* stream);
+size_t ia2c_host_tape_bytes(const ia2c_episode_desc* d);
+size_t ia2c_host_result_bytes(const ia2c_episode_desc* d);
+int ia2c_train_episodes_host(const ia2c_episode_desc* d, void* stage_b, int32_t n_episodes, const void* const* host_tapes,
+                             void* host_results, void* stream);
 
 #ifdef __cplusplus
 }

@@ -192,7 +192,7 @@ def test_pipelined_host_episodes_match_sequential_calls():
     ub = [torch.from_numpy(rng.rand(T + 1, E, N, N - 1)).pin_memory() for _ in range(n)]
     a = make_trainer(E, N, M, init, fused_rollout=True)
     b = make_trainer(E, N, M, init, fused_rollout=True)
-    piped = a.train_episodes_host(ua, ub)
+    piped = a.train_episodes_host([a.pack_host_tape(x, y) for x, y in zip(ua, ub)])
     seq = [b.train_episode_host(x, y) for x, y in zip(ua, ub)]
     for p, q in zip(piped, seq):
         assert np.array_equal(p["ep_return"], q["ep_return"]) and np.array_equal(p["critic_loss"], q["critic_loss"])
