@@ -348,11 +348,20 @@ def run_ours(args):
     barrier()
     e2e_wall_ms = (time.perf_counter() - t0) * 1e3
     e2e_ms = max_over_ranks(max(s.elapsed_time(e), e2e_wall_ms))
+    # keep the same load running until the clock sampler (rank 0) has data; the decision is COLLECTIVE so that every rank
+    # runs the same number of extra episodes (the gradient exchange needs all ranks in every episode)
+    for _ in range(50):
+        need = 1 if (sampler is not None and sampler.n_samples() - sampler.marks[0] < 5) else 0
+        if dist is not None:
+            flag = torch.tensor([need], dtype=torch.int32, device=dev)
+            dist.broadcast(flag, 0)
+            need = int(flag.item())
+        if not need:
+            break
+        for _ in range(200):
+            tr.train_episode()
+        torch.cuda.synchronize()
     if sampler:
-        while sampler.n_samples() - sampler.marks[0] < 5:   # keep the same load running until the sampler has data
-            for _ in range(200):
-                tr.train_episode()
-            torch.cuda.synchronize()
         sampler.mark()
     tr.inject()  # back to the device Philox streams
     clocks = sampler.stop() if sampler else None
