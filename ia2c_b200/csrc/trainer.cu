@@ -7,17 +7,20 @@
 // generalised from 2 to N agents as specified in DESIGN.md ("Org-N"; identical to the reference at N=2).
 //
 // Kernels in this file
-//   rollout_step_kernel   one time step for all envs: Org transition from act[t-1] (counts reduced by
-//                         warp shuffles, agents in lanes), observation, every agent's actor forward +
-//                         sample -> act[t], true-partner mode.  Per-agent actor weights staged in smem.
-//   critic_grad_kernel    per (agent, row): Q(obs), Q(next_obs), TD target with gradient through both
-//                         passes (residual gradient), closed-form backward accumulated in
-//                         registers, block-reduced to partials (fixed order).
-//   actor_grad_kernel     per (agent, row): advantage from the updated critic (2 critic forwards), actor
-//                         forward, Categorical log-prob/entropy loss, closed-form backward, partials.
-//   reduce_adam_kernel    sums the partials, writes grad (+loss), and applies Adam (actor: accumulating
-//                         gradient buffer).
-// The belief update between steps is belief_pairs_kernel (belief.cu).
+//   rollout_step_kernel    one time step for all envs (general N): Org transition from act[t-1] (counts reduced by
+//                          warp shuffles, agents in lanes), observation, every agent's actor forward + sample ->
+//                          act[t], true-partner mode.  Per-agent actor weights staged in smem.  (N <= 8 uses the
+//                          persistent pipelined kernel of rollout_fused.cu instead.)
+//   critic_grad_kernel     a thread walks a time chunk of one (agent, env): ONE critic forward and ONE backward per
+//                          observation (TD target with gradient through both passes: residual gradient, SURVEY.md
+//                          Q8), FFMA2 math, accumulators in registers, block-reduced to partials (fixed order).
+//                          Skipped when the fused rollout already produced the critic partials.
+//   actor_grad_kernel      same walk: advantage from the updated critic, actor forward, Categorical
+//                          log-prob/entropy loss, closed-form backward, partials.
+//   reduce_adam_kernel     sums the partials, writes grad (+loss), applies Adam (actor: accumulating gradient
+//                          buffer).
+//   allreduce_adam_kernel  multi-GPU: the same plus the gradient exchange over NVLink peer memory, in one kernel.
+// The belief update between steps is belief_pairs(_table)_kernel (belief.cu).
 #include <algorithm>
 
 #include "common.cuh"
@@ -150,13 +153,6 @@ __global__ void __launch_bounds__(kRolloutThreads) rollout_step_kernel(StepArgs 
             pt[i] = (uint8_t)mode3(c0 - (a == 0), c1 - (a == 1), c2 - (a == 2));
         }
     }
-}
-
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void load_obs(const float* __restrict__ p, float (&x)[F]) {
-    const float2* p2 = reinterpret_cast<const float2*>(p);
-    const float2 a = __ldg(p2), b = __ldg(p2 + 1), c = __ldg(p2 + 2);
-    x[0] = a.x; x[1] = a.y; x[2] = b.x; x[3] = b.y; x[4] = c.x; x[5] = c.y;
 }
 
 // ---- gradient kernels: one thread per (agent, env, time chunk), packed fp32 math (mlp_f2.cuh) ----------
