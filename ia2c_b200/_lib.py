@@ -18,6 +18,7 @@ FLAG_FUSED_ROLLOUT = 1
 FLAG_SKIP_ADAM = 2
 FLAG_FUSED_CRITIC = 4
 FLAG_GRAD_ONLY = 8
+FLAG_ACTOR_COLUMNS = 16
 BELIEF_RECORD = 8
 ACTOR_P = 105
 CRITIC_P = 147

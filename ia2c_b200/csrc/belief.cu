@@ -197,8 +197,7 @@ __global__ void __launch_bounds__(kThreads) belief_pairs_kernel(PairsArgs P) {
 #pragma unroll
         for (int a = 0; a < A; ++a) lik[a] = (a == seen) ? 0.8 : 0.1;   // ia2c.py:53-58
         const double u = P.u_injected ? P.u_injected[rec]
-                                      : philox_uniform_f64(P.seed, kStreamBelief, P.episode, P.t,
-                                                           (uint64_t)(((P.env_offset + e) * N + i) * (int64_t)K + jj));
+                                      : philox_belief_uniform(P.seed, P.episode, P.t, (uint64_t)((P.env_offset + e) * N + i), K, jj);
         double b[M], pred[A];
         const int ap = belief_core<M, A>(fa + il * M * A, lik, prev, u, b, pred);
         uint32_t lo = 0, hi = 0;
@@ -245,7 +244,9 @@ __global__ void debug_divide_kernel(const double* __restrict__ a, const double* 
 //      order) and each record needs M table lookups instead of 6M multiply/adds;
 //  (2) the mixture prediction is only COMPARED with u.  It is evaluated in fp32 (a different pipe); when u lies
 //      within 1e-5 of a decision boundary — the fp32 error is below 1e-6 — the record falls back to the exact
-//      fp64 sequence.  The fallback rate is ~6e-5 per record.
+//      fp64 sequence.  The fallback rate is ~6e-5 per record;
+//  (3) the posterior is stored rounded to hundredths, so the M IEEE divisions are replaced by multiplications with the
+//      shared reciprocal plus a fixed-point test that proves the rounding agrees (exact fallback otherwise).
 // Per record that leaves S, one shared reciprocal, M corrected divisions and M roundings on the fp64 pipe.
 // Block = (agent i, chunk of envs): the agent's K records of one env are 8*K contiguous bytes.
 template <int M>
@@ -280,16 +281,17 @@ __global__ void __launch_bounds__(kThreads) belief_pairs_table_kernel(PairsArgs 
     }
     __syncthreads();
     const int prior_k = (int)rint(100.0 / M);
-    const int total = n_envs * K;
-    for (int q = threadIdx.x; q < total; q += blockDim.x) {
-        const int el = q / K, jj = q - el * K;
+    // One thread = one PAIR of modelled-other slots (2s, 2s+1) of one env: the two records share a Philox block and
+    // give the scheduler two independent chains.
+    const int KP = (K + 1) >> 1;
+    const float inv_kp = 1.f / (float)KP;
+    const int total = n_envs * KP;
+    auto one_record = [&](int64_t rec, int el, int jj, double u) -> int {
         const int j = jj + (jj >= i);
-        const int64_t e = e0 + el;
-        const int64_t rec = (e * N + i) * (int64_t)K + jj;
         uint2 raw = make_uint2(0u, 0u);
         if (!P.reset_prior) raw = *reinterpret_cast<const uint2*>(P.records + rec * IA2C_BELIEF_RECORD);
         const double* row = bpt + act[el * N + j] * (M * 101);
-        double bp[M], b[M];
+        double bp[M];
 #pragma unroll
         for (int m = 0; m < M; ++m) {
             const uint32_t word = m < 4 ? raw.x : raw.y;
@@ -300,19 +302,31 @@ __global__ void __launch_bounds__(kThreads) belief_pairs_table_kernel(PairsArgs 
 #pragma unroll
         for (int m = 1; m < M; ++m) S = __dadd_rn(S, bp[m]);
         const double rS = drcp_seq(S);
-        uint32_t lo = 0, hi = 0;
+        // (3) screened quotients: q~ = bp * (1/S) is within 4e-16 of the IEEE quotient b = bp / S, and the posterior is
+        //     only used ROUNDED to hundredths: z = rint(q~ * 100 * 2^20) is 100*b in fixed point, exact to 1e-6; unless
+        //     its fraction is within 2^-19 of one half, rint(100*q~) == rint(100*b) and the M divisions are skipped.
+        uint32_t kq[M];
         float bf[M];
+        bool near_half = false;
 #pragma unroll
         for (int m = 0; m < M; ++m) {
-            b[m] = ddiv_with(bp[m], S, rS);
-            bf[m] = (float)b[m];
-            const uint32_t k = (uint32_t)__double2int_rn(__dmul_rn(b[m], 100.0));
-            if (m < 4) lo |= k << (8 * m); else hi |= k << (8 * (m - 4));
-            if (P.belief_out) P.belief_out[rec * M + m] = (uint8_t)k;
+            const double qa = __dmul_rn(bp[m], rS);
+            const int z = __double2int_rn(__dmul_rn(qa, 104857600.0));   // 100 * 2^20, exact scaling
+            bf[m] = (float)qa;
+            kq[m] = (uint32_t)(z + (1 << 19)) >> 20;
+            const int frac = z & ((1 << 20) - 1);
+            near_half |= (unsigned)(frac - (1 << 19) + 2) <= 4u;
         }
-        const double u = P.u_injected ? P.u_injected[rec]
-                                      : philox_uniform_f64(P.seed, kStreamBelief, P.episode, P.t,
-                                                           (uint64_t)(((P.env_offset + e) * N + i) * (int64_t)K + jj));
+        if (near_half) {   // exact path (identical to belief_core): ~1e-5 of the records
+#pragma unroll
+            for (int m = 0; m < M; ++m) kq[m] = (uint32_t)__double2int_rn(__dmul_rn(ddiv_with(bp[m], S, rS), 100.0));
+        }
+        uint32_t lo = 0, hi = 0;
+#pragma unroll
+        for (int m = 0; m < M; ++m) {
+            if (m < 4) lo |= kq[m] << (8 * m); else hi |= kq[m] << (8 * (m - 4));
+            if (P.belief_out) P.belief_out[rec * M + m] = (uint8_t)kq[m];
+        }
         // fp32 screening of the inverse-CDF decision
         float pf[A];
 #pragma unroll
@@ -333,6 +347,9 @@ __global__ void __launch_bounds__(kThreads) belief_pairs_table_kernel(PairsArgs 
             if (!found && uf < cf) { ap = a; found = true; }
         }
         if (risky) {   // exact sequence, identical to belief_core
+            double b[M];
+#pragma unroll
+            for (int m = 0; m < M; ++m) b[m] = ddiv_with(bp[m], S, rS);
             double c = 0.0;
             ap = 0;
             found = false;
@@ -349,6 +366,24 @@ __global__ void __launch_bounds__(kThreads) belief_pairs_table_kernel(PairsArgs 
         *reinterpret_cast<uint2*>(P.records + rec * IA2C_BELIEF_RECORD) = make_uint2(lo, hi);
         if (P.pred_out) P.pred_out[rec] = (uint8_t)ap;
         if (P.pred_partner_out) atomicAdd(&counts[el * A + ap], 1);   // ptxas aggregates same-address lanes (REDUX)
+        return ap;
+    };
+    for (int q = threadIdx.x; q < total; q += blockDim.x) {
+        const int el = (int)(((float)q + 0.5f) * inv_kp);   // q / KP (exact: q < 2^16, margin 0.5/KP)
+        const int sl = q - el * KP;
+        const int jj = 2 * sl;
+        const bool two = jj + 1 < K;
+        const int64_t e = e0 + el;
+        const int64_t rec = (e * N + i) * (int64_t)K + jj;
+        double u0, u1 = 0.0;
+        if (P.u_injected) {
+            u0 = P.u_injected[rec];
+            if (two) u1 = P.u_injected[rec + 1];
+        } else {
+            philox_belief_pair(P.seed, P.episode, P.t, (uint64_t)((P.env_offset + e) * N + i), K, sl, u0, u1);
+        }
+        one_record(rec, el, jj, u0);
+        if (two) one_record(rec + 1, el, jj + 1, u1);
     }
     if (P.pred_partner_out) {
         __syncthreads();

@@ -95,12 +95,18 @@ __global__ void __launch_bounds__(kBlock) rollout_fused_kernel(ia2c_episode_desc
             ua_s[t & 1][lane] = d.inj_u_action ? d.inj_u_action[row]
                                                : philox_uniform_f32(d.seed, kStreamAction, d.episode, (uint32_t)t,
                                                                     (uint64_t)((d.env_offset + e) * N + i));
+            if (d.inj_u_belief) {
 #pragma unroll
-            for (int jj = 0; jj < K; ++jj)
-                ub_s[t & 3][jj][lane] =
-                    d.inj_u_belief ? d.inj_u_belief[row * K + jj]
-                                   : philox_uniform_f64(d.seed, kStreamBelief, d.episode, (uint32_t)t,
-                                                        (uint64_t)(((d.env_offset + e) * N + i) * (int64_t)K + jj));
+                for (int jj = 0; jj < K; ++jj) ub_s[t & 3][jj][lane] = d.inj_u_belief[row * K + jj];
+            } else {
+#pragma unroll
+                for (int sl = 0; sl < (K + 1) / 2; ++sl) {
+                    double u0, u1;
+                    philox_belief_pair(d.seed, d.episode, (uint32_t)t, (uint64_t)((d.env_offset + e) * N + i), K, sl, u0, u1);
+                    ub_s[t & 3][2 * sl][lane] = u0;
+                    if (2 * sl + 1 < K) ub_s[t & 3][2 * sl + 1][lane] = u1;
+                }
+            }
         }
     };
 

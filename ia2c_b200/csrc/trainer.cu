@@ -30,6 +30,8 @@ namespace ia2c {
 int rollout_fused_supported(int N, int M);                                  // rollout_fused.cu
 int rollout_fused_launch(const ia2c_episode_desc* d, cudaStream_t s);
 int64_t rollout_fused_blocks(int64_t E, int N);
+int actor_pipe_launch(const ia2c_episode_desc* d, cudaStream_t s);
+int64_t actor_pipe_blocks(int64_t E, int N);
 
 namespace {
 
@@ -435,9 +437,22 @@ static int critic_partial_blocks(const ia2c_episode_desc* d) {
     return fused_critic(d) ? (int)rollout_fused_blocks(d->E, d->N) : grad_blocks(d);
 }
 
+// the actor-gradient producer: the pipelined kernel (actor_pipe.cu) unless the caller asks for the column kernel
+static bool actor_columns(const ia2c_episode_desc* d) { return d->flags & IA2C_FLAG_ACTOR_COLUMNS; }
+static int actor_partial_blocks(const ia2c_episode_desc* d) {
+    return actor_columns(d) ? grad_blocks(d) : (int)actor_pipe_blocks(d->E, d->N);
+}
+static int launch_actor_grad(const ia2c_episode_desc* d, cudaStream_t s) {
+    if (!actor_columns(d)) return actor_pipe_launch(d, s);
+    dim3 grid(grad_blocks(d), d->N);
+    actor_grad_kernel<<<grid, kGradThreads, 0, s>>>(*d, d->partials);
+    return check_launch("actor_grad_kernel");
+}
+
 extern "C" size_t ia2c_episode_partials_floats(const ia2c_episode_desc* d) {
     if (!d || d->N < 1 || d->E < 1 || d->T < 1) return 0;
-    const size_t blocks = (size_t)std::max<int64_t>(grad_blocks(d), rollout_fused_blocks(d->E, std::min(d->N, 8)));
+    const size_t blocks = (size_t)std::max<int64_t>(std::max<int64_t>(grad_blocks(d), (d->E + 31) / 32),
+                                                    rollout_fused_blocks(d->E, std::min(d->N, 8)));
     return (size_t)d->N * blocks * (kCriticP + 1);
 }
 
@@ -487,7 +502,7 @@ extern "C" int ia2c_rollout(const ia2c_episode_desc* d, void* stream) {
 static int run_reduce(const ia2c_episode_desc* d, int which, int from_partials, int apply, cudaStream_t s) {
     ReduceArgs R;
     R.partials = d->partials;
-    R.n_blocks = which == 0 ? critic_partial_blocks(d) : grad_blocks(d);
+    R.n_blocks = which == 0 ? critic_partial_blocks(d) : actor_partial_blocks(d);
     R.P = which == 0 ? kCriticP : kActorP;
     R.grad = which == 0 ? d->critic_grad : d->actor_grad;
     R.grad_accum = which == 0 ? nullptr : d->actor_grad_accum;
@@ -638,9 +653,7 @@ extern "C" int ia2c_actor_phase(const ia2c_episode_desc* d, void* stream) {
     if (int rc = validate(d, "ia2c_actor_phase")) return rc;
     if (int rc = check_update_ptrs(d, "ia2c_actor_phase")) return rc;
     cudaStream_t s = as_stream(stream);
-    dim3 grid(grad_blocks(d), d->N);
-    actor_grad_kernel<<<grid, kGradThreads, 0, s>>>(*d, d->partials);
-    if (int rc = check_launch("actor_grad_kernel")) return rc;
+    if (int rc = launch_actor_grad(d, s)) return rc;
     if (d->flags & IA2C_FLAG_GRAD_ONLY) return 0;
     return run_reduce(d, 1, 1, !(d->flags & IA2C_FLAG_SKIP_ADAM), s);
 }
@@ -782,7 +795,7 @@ extern "C" int ia2c_train_episode_timed(const ia2c_episode_desc* d, float* host_
     cudaEventRecord(ev[2], s);
     if (!rc) rc = run_reduce(d, 0, 1, apply, s);
     cudaEventRecord(ev[3], s);
-    if (!rc) { actor_grad_kernel<<<grid, kGradThreads, 0, s>>>(*d, d->partials); rc = check_launch("actor_grad_kernel"); }
+    if (!rc) rc = launch_actor_grad(d, s);
     cudaEventRecord(ev[4], s);
     if (!rc) rc = run_reduce(d, 1, 1, apply, s);
     cudaEventRecord(ev[5], s);
@@ -814,7 +827,7 @@ extern "C" int ia2c_allreduce_adam(const ia2c_episode_desc* d, int32_t which, co
     cudaStream_t s = as_stream(stream);
     ReduceArgs R;
     R.partials = d->partials;
-    R.n_blocks = which == 0 ? critic_partial_blocks(d) : grad_blocks(d);
+    R.n_blocks = which == 0 ? critic_partial_blocks(d) : actor_partial_blocks(d);
     R.P = which == 0 ? kCriticP : kActorP;
     R.grad = which == 0 ? d->critic_grad : d->actor_grad;
     R.grad_accum = which == 0 ? nullptr : d->actor_grad_accum;

@@ -50,8 +50,10 @@ class IA2CTrainer:
     def __init__(self, num_envs, n_agents=2, n_models=5, steps_per_episode=30, max_episode_steps=30,
                  lr_critic=0.0002, lr_actor=0.0001, beta=0.001, gamma=0.9, seed=0, device=None,
                  rank=0, world_size=1, process_group=None, dumps=False, fused_rollout=False, fused_critic=None,
-                 init=None, comm="auto"):
+                 init=None, comm="auto", actor_kernel="pipe"):
         _lib.require_cuda()
+        if actor_kernel not in ("pipe", "columns"):
+            raise ValueError("actor_kernel must be 'pipe' or 'columns'")
         self.lib = _lib.load()
         self.rank, self.world = int(rank), int(world_size)
         self.pg = process_group
@@ -100,7 +102,8 @@ class IA2CTrainer:
         if fused_critic is None:
             fused_critic = bool(fused_rollout)   # the critic-gradient stage rides along with the fused rollout
         d.flags = ((_lib.FLAG_FUSED_ROLLOUT if fused_rollout else 0) | (_lib.FLAG_SKIP_ADAM if self.world > 1 else 0) |
-                   (_lib.FLAG_FUSED_CRITIC if (fused_rollout and fused_critic) else 0))
+                   (_lib.FLAG_FUSED_CRITIC if (fused_rollout and fused_critic) else 0) |
+                   (_lib.FLAG_ACTOR_COLUMNS if actor_kernel == "columns" else 0))
         for name in ("actor_params", "actor_grad", "actor_grad_accum", "actor_m", "actor_v", "critic_params",
                      "critic_grad", "critic_m", "critic_v", "actor_step", "critic_step", "loss_out", "filter_action",
                      "env_state", "env_hist", "env_cls", "env_elapsed", "ep_return", "obs", "reward", "act",

@@ -213,6 +213,7 @@ typedef struct ia2c_episode_desc {
                                        (ia2c_critic_phase then only reduces the partials and applies Adam) */
 #define IA2C_FLAG_GRAD_ONLY     8   /* critic/actor phase stop after the gradient kernel (per-block partials only);
                                        ia2c_allreduce_adam then reduces, exchanges and steps */
+#define IA2C_FLAG_ACTOR_COLUMNS 16  /* actor phase: use the time-chunk column kernel instead of the pipelined one (A/B, parity tests) */
 #define IA2C_FLAG_SKIP_ADAM     2   /* stop after writing gradients (multi-GPU: all-reduce, then ia2c_adam_step) */
 
 size_t ia2c_episode_partials_floats(const ia2c_episode_desc* d);

@@ -54,8 +54,24 @@ def uniform_f32(seed, stream, episode, t, index):
     return ((x0 >> np.uint32(8)).astype(np.float32)) * np.float32(2.0 ** -24)
 
 
-def uniform_f64(seed, stream, episode, t, index):
-    """53-bit uniform in [0,1) as float64 (belief sampler; same resolution as np.random.rand)."""
-    x0, x1, _, _ = draw(seed, stream, episode, t, index)
-    bits = (x0.astype(np.uint64) << np.uint64(32)) | x1.astype(np.uint64)
+def _unit_f64(hi, lo):
+    bits = (hi.astype(np.uint64) << np.uint64(32)) | lo.astype(np.uint64)
     return (bits >> np.uint64(11)).astype(np.float64) * (2.0 ** -53)
+
+
+def uniform_f64(seed, stream, episode, t, index):
+    """53-bit uniform in [0,1) as float64 from words (x0, x1) (same resolution as np.random.rand)."""
+    x0, x1, _, _ = draw(seed, stream, episode, t, index)
+    return _unit_f64(x0, x1)
+
+
+def belief_uniforms(seed, episode, t, rows, K):
+    """The belief sampler's uniforms u[..., jj] for belief rows `rows` (= env * N + agent, any shape) and K modelled
+    others.  One Philox block serves two slots (common.cuh: philox_belief_pair): slots (2s, 2s+1) of row r share
+    the draw at index r * ceil(K/2) + s; words (x0, x1) -> slot 2s, (x2, x3) -> slot 2s+1."""
+    rows = np.asarray(rows, dtype=np.uint64)
+    kp = (K + 1) // 2
+    idx = rows[..., None] * np.uint64(kp) + np.arange(kp, dtype=np.uint64)
+    x0, x1, x2, x3 = draw(seed, STREAM_BELIEF, episode, t, idx)
+    u = np.stack([_unit_f64(x0, x1), _unit_f64(x2, x3)], axis=-1).reshape(rows.shape + (2 * kp,))
+    return u[..., :K]

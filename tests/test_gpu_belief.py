@@ -84,7 +84,7 @@ def _pairs_oracle(fa, act, prior, u):
     return ap, bp
 
 
-@pytest.mark.parametrize("E,N,M", [(1, 2, 5), (37, 2, 5), (300, 3, 5), (9, 5, 3), (5, 64, 5), (2, 256, 5), (3, 7, 6), (4, 6, 2)])
+@pytest.mark.parametrize("E,N,M", [(1, 2, 5), (37, 2, 5), (300, 3, 5), (9, 5, 3), (5, 64, 5), (2, 256, 5), (3, 7, 6), (4, 6, 2), (3, 65, 5), (70, 33, 5), (40, 130, 5)])
 def test_pairs_kernel_vs_oracle(E, N, M):
     import torch
     from ia2c_b200 import _lib
@@ -101,7 +101,7 @@ def test_pairs_kernel_vs_oracle(E, N, M):
         if injected:
             u = rng.rand(E, N, K)
         else:
-            u = P.uniform_f64(77, P.STREAM_BELIEF, 5, t, (np.arange(E)[:, None, None] + 1000) * N * K + np.arange(N)[None, :, None] * K + np.arange(K)[None, None, :])
+            u = P.belief_uniforms(77, 5, t, (np.arange(E)[:, None] + 1000) * N + np.arange(N)[None, :], K)
         pred = torch.empty(E, N, K, dtype=torch.uint8, device="cuda")
         bel = torch.empty(E, N, K, M, dtype=torch.uint8, device="cuda")
         partner = torch.empty(E, N, dtype=torch.uint8, device="cuda")

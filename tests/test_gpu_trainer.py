@@ -110,9 +110,8 @@ def test_philox_mode_is_replayable_by_the_oracle():
     for ep in range(2):
         tr.train_episode(sync_stats=True)
         idx_a = np.arange(E)[:, None] * N + np.arange(N)[None, :]
-        idx_b = (np.arange(E)[:, None, None] * N + np.arange(N)[None, :, None]) * (N - 1) + np.arange(N - 1)[None, None, :]
         u_act = np.stack([P.uniform_f32(seed, P.STREAM_ACTION, ep, t, idx_a) for t in range(T + 1)])
-        u_bel = np.stack([P.uniform_f64(seed, P.STREAM_BELIEF, ep, t, idx_b) for t in range(T + 1)])
+        u_bel = np.stack([P.belief_uniforms(seed, ep, t, idx_a, N - 1) for t in range(T + 1)])
         gpu_actions = host(tr.act).astype(np.int64)
         probe = L.IA2CState(actor=st.actor.copy(), critic=st.critic.copy(), filter_action=fa, T=T)
         resampled = L.ia2c_rollout(probe, E, u_act=u_act, u_belief=u_bel)["act"]
@@ -174,6 +173,26 @@ def test_fused_rollout_matches_per_step_path(E, N, M, mode, fused_critic):
                 for name in UPDATE_OUTPUTS:
                     assert rel_err(host(getattr(b, name)), host(getattr(a, name))) < 2e-6, (name, ep)
                 assert rel_err(lb["critic_loss"], la["critic_loss"]) < 2e-6 and rel_err(lb["actor_loss"], la["actor_loss"]) < 2e-6
+
+
+@pytest.mark.parametrize("E,N,M,T", [(1, 2, 5, 30), (100, 2, 5, 30), (4096, 2, 5, 30), (33, 3, 5, 12), (40, 33, 5, 6), (65, 5, 5, 1), (31, 2, 3, 2), (4100, 2, 5, 7), (2500, 3, 5, 3)])
+def test_pipelined_actor_gradient_matches_column_kernel(E, N, M, T):
+    """actor_pipe.cu (warp-specialised pipeline over time) against the time-chunk column kernel on the same
+    trajectories: same advantages bit for bit, gradients/losses equal up to the summation order."""
+    init = _random_init(N, M, seed=E + T)
+    a = make_trainer(E, N, M, init, seed=3, steps_per_episode=T, max_episode_steps=T, actor_kernel="columns")
+    b = make_trainer(E, N, M, init, seed=3, steps_per_episode=T, max_episode_steps=T, actor_kernel="pipe")
+    rng = np.random.RandomState(E * N)
+    for ep in range(2):
+        actions, u = rng.randint(0, 3, size=(T + 1, E, N)), rng.rand(T + 1, E, N, N - 1)
+        a.inject(actions=actions, u_belief=u), b.inject(actions=actions, u_belief=u)
+        la, lb = a.train_episode(sync_stats=True), b.train_episode(sync_stats=True)
+        if ep == 0:
+            assert np.array_equal(host(a.adv_dump), host(b.adv_dump))
+        for name in ("adv_dump", "actor_grad", "actor_grad_accum", "actor_params"):
+            assert rel_err(host(getattr(b, name)), host(getattr(a, name))) < 1e-5, (name, ep)
+        assert rel_err(lb["actor_loss"], la["actor_loss"]) < 1e-5
+        assert np.array_equal(host(a.actor_step), host(b.actor_step))
 
 
 def test_fused_rollout_rejects_unsupported_shapes():
