@@ -249,9 +249,15 @@ __global__ void debug_divide_kernel(const double* __restrict__ a, const double* 
 //      shared reciprocal plus a fixed-point test that proves the rounding agrees (exact fallback otherwise).
 // Per record that leaves S, one shared reciprocal, M corrected divisions and M roundings on the fp64 pipe.
 // Block = (agent i, chunk of envs): the agent's K records of one env are 8*K contiguous bytes.
-template <int M>
-__global__ void __launch_bounds__(kThreads) belief_pairs_table_kernel(PairsArgs P) {
+// FAST = the steady-state call of the rollout (device Philox, no dumps, priors from the records): the optional
+// pointers are compiled out instead of costing a predicated-off instruction each per record.
+template <int M, bool FAST>
+__global__ void __launch_bounds__(kThreads, 4) belief_pairs_table_kernel(PairsArgs P) {
     constexpr int A = IA2C_AGENT_ACTIONS;
+    const bool reset_prior = !FAST && P.reset_prior;
+    const double* const u_injected = FAST ? nullptr : P.u_injected;
+    uint8_t* const belief_out = FAST ? nullptr : P.belief_out;
+    uint8_t* const pred_out = FAST ? nullptr : P.pred_out;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int N = P.N, K = P.K, i = blockIdx.y;
     const int EC = P.envs_per_block;
@@ -286,16 +292,14 @@ __global__ void __launch_bounds__(kThreads) belief_pairs_table_kernel(PairsArgs 
     const int KP = (K + 1) >> 1;
     const float inv_kp = 1.f / (float)KP;
     const int total = n_envs * KP;
-    auto one_record = [&](int64_t rec, int el, int jj, double u) -> int {
+    auto one_record = [&](int64_t rec, int el, int jj, double u, uint2 raw) -> int {
         const int j = jj + (jj >= i);
-        uint2 raw = make_uint2(0u, 0u);
-        if (!P.reset_prior) raw = *reinterpret_cast<const uint2*>(P.records + rec * IA2C_BELIEF_RECORD);
         const double* row = bpt + act[el * N + j] * (M * 101);
         double bp[M];
 #pragma unroll
         for (int m = 0; m < M; ++m) {
             const uint32_t word = m < 4 ? raw.x : raw.y;
-            const int k = P.reset_prior ? prior_k : (int)((word >> (8 * (m & 3))) & 0xFFu);
+            const int k = reset_prior ? prior_k : (int)((word >> (8 * (m & 3))) & 0xFFu);
             bp[m] = row[m * 101 + k];
         }
         double S = bp[0];
@@ -325,7 +329,7 @@ __global__ void __launch_bounds__(kThreads) belief_pairs_table_kernel(PairsArgs 
 #pragma unroll
         for (int m = 0; m < M; ++m) {
             if (m < 4) lo |= kq[m] << (8 * m); else hi |= kq[m] << (8 * (m - 4));
-            if (P.belief_out) P.belief_out[rec * M + m] = (uint8_t)kq[m];
+            if (belief_out) belief_out[rec * M + m] = (uint8_t)kq[m];
         }
         // fp32 screening of the inverse-CDF decision
         float pf[A];
@@ -364,26 +368,42 @@ __global__ void __launch_bounds__(kThreads) belief_pairs_table_kernel(PairsArgs 
         }
         hi |= (uint32_t)ap << 16;  // byte 6
         *reinterpret_cast<uint2*>(P.records + rec * IA2C_BELIEF_RECORD) = make_uint2(lo, hi);
-        if (P.pred_out) P.pred_out[rec] = (uint8_t)ap;
-        if (P.pred_partner_out) atomicAdd(&counts[el * A + ap], 1);   // ptxas aggregates same-address lanes (REDUX)
+        if (pred_out) pred_out[rec] = (uint8_t)ap;
+        if (FAST || P.pred_partner_out) atomicAdd(&counts[el * A + ap], 1);   // ptxas aggregates same-address lanes (REDUX)
         return ap;
     };
+    // the two records of the NEXT iteration are fetched before the current pair is processed (software prefetch: the
+    // kernel is bound by the latency of these loads at 4 blocks per SM).
+    struct Slot { int el, sl; int64_t rec; uint2 raw0, raw1; };
+    auto locate = [&](int q, Slot& s) {
+        s.el = (int)(((float)q + 0.5f) * inv_kp);   // q / KP (exact: q < 2^16, margin 0.5/KP)
+        s.sl = q - s.el * KP;
+        s.rec = ((e0 + s.el) * N + i) * (int64_t)K + 2 * s.sl;
+        s.raw0 = s.raw1 = make_uint2(0u, 0u);
+        if (!reset_prior) {
+            const uint2* rp = reinterpret_cast<const uint2*>(P.records + s.rec * IA2C_BELIEF_RECORD);
+            s.raw0 = rp[0];
+            if (2 * s.sl + 1 < K) s.raw1 = rp[1];
+        }
+    };
+    Slot cur;
+    if ((int)threadIdx.x < total) locate(threadIdx.x, cur);
     for (int q = threadIdx.x; q < total; q += blockDim.x) {
-        const int el = (int)(((float)q + 0.5f) * inv_kp);   // q / KP (exact: q < 2^16, margin 0.5/KP)
-        const int sl = q - el * KP;
-        const int jj = 2 * sl;
+        Slot nxt = cur;
+        if (q + (int)blockDim.x < total) locate(q + blockDim.x, nxt);
+        const int el = cur.el, sl = cur.sl, jj = 2 * sl;
         const bool two = jj + 1 < K;
-        const int64_t e = e0 + el;
-        const int64_t rec = (e * N + i) * (int64_t)K + jj;
+        const int64_t e = e0 + el, rec = cur.rec;
         double u0, u1 = 0.0;
-        if (P.u_injected) {
-            u0 = P.u_injected[rec];
-            if (two) u1 = P.u_injected[rec + 1];
+        if (u_injected) {
+            u0 = u_injected[rec];
+            if (two) u1 = u_injected[rec + 1];
         } else {
             philox_belief_pair(P.seed, P.episode, P.t, (uint64_t)((P.env_offset + e) * N + i), K, sl, u0, u1);
         }
-        one_record(rec, el, jj, u0);
-        if (two) one_record(rec + 1, el, jj + 1, u1);
+        one_record(rec, el, jj, u0, cur.raw0);
+        if (two) one_record(rec + 1, el, jj + 1, u1, cur.raw1);
+        cur = nxt;
     }
     if (P.pred_partner_out) {
         __syncthreads();
@@ -404,9 +424,15 @@ int launch_pairs_table(PairsArgs& P, cudaStream_t stream) {
     size_t smem = (104 + 3 * M * 101 + M * 3) * sizeof(double) + ((M * 3 + 3) & ~3) * sizeof(float) +
                   (size_t)P.envs_per_block * 3 * sizeof(int) + (size_t)P.envs_per_block * P.N;
     smem = (smem + 15) & ~size_t(15);
-    if (smem > 48 * 1024) cudaFuncSetAttribute(belief_pairs_table_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     dim3 grid((unsigned)env_blocks, P.N);
-    belief_pairs_table_kernel<M><<<grid, kThreads, smem, stream>>>(P);
+    const bool fast = !P.reset_prior && !P.u_injected && !P.belief_out && !P.pred_out && P.pred_partner_out;
+    if (fast) {
+        if (smem > 48 * 1024) cudaFuncSetAttribute(belief_pairs_table_kernel<M, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        belief_pairs_table_kernel<M, true><<<grid, kThreads, smem, stream>>>(P);
+    } else {
+        if (smem > 48 * 1024) cudaFuncSetAttribute(belief_pairs_table_kernel<M, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        belief_pairs_table_kernel<M, false><<<grid, kThreads, smem, stream>>>(P);
+    }
     return check_launch("belief_pairs_table_kernel");
 }
 

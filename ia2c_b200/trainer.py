@@ -50,10 +50,12 @@ class IA2CTrainer:
     def __init__(self, num_envs, n_agents=2, n_models=5, steps_per_episode=30, max_episode_steps=30,
                  lr_critic=0.0002, lr_actor=0.0001, beta=0.001, gamma=0.9, seed=0, device=None,
                  rank=0, world_size=1, process_group=None, dumps=False, fused_rollout=False, fused_critic=None,
-                 init=None, comm="auto", actor_kernel="pipe"):
+                 init=None, comm="auto", actor_kernel="auto"):
         _lib.require_cuda()
-        if actor_kernel not in ("pipe", "columns"):
-            raise ValueError("actor_kernel must be 'pipe' or 'columns'")
+        if actor_kernel not in ("auto", "pipe", "columns"):
+            raise ValueError("actor_kernel must be 'auto', 'pipe' or 'columns'")
+        if actor_kernel == "auto":   # measured (tools/time_kernels.py): columns 22.6 vs pipe 26.5 us at 4096 x 2;
+            actor_kernel = "pipe" if int(n_agents) > 64 else "columns"   # equal at 1024 x 64; pipe 395 vs 479 us at 1024 x 256
         self.lib = _lib.load()
         self.rank, self.world = int(rank), int(world_size)
         self.pg = process_group
