@@ -373,7 +373,7 @@ def run_ours(args):
     traj_bytes = (T + 1) * E_gpu * (24 + 3 * N) + T * E_gpu * 4 + E_gpu * (26 + 8 * N * (N - 1))
     if fused:   # + the critic-gradient partials the fused critic stage writes (one 148-float row per block and agent)
         traj_bytes += (E_gpu * (2 if N <= 2 else 4 if N <= 4 else 8) // 32) * N * 148 * 4
-    kname = "rollout_fused_kernel (rollout + critic gradient)" if fused else "rollout_step_kernel + belief_pairs_kernel (x31)"
+    kname = "rollout_fused_kernel (rollout + critic gradient)" if fused else "env_step_kernel + actor_step_kernel + belief_pairs_kernel (x31)"
     achieved = traj_bytes / (rollout_us * 1e-6) / 1e9
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,

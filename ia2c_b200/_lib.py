@@ -75,6 +75,7 @@ SIGNATURES = {
     "ia2c_loss_workspace": (C.c_size_t, [i64]),
     "ia2c_adam_step": (C.c_int, [vp, vp, vp, vp, vp, vp, f64, f64, f64, f64, i32, i32, vp]),
     "ia2c_episode_partials_floats": (C.c_size_t, [_DP]),
+    "ia2c_rollout_fused_supported": (C.c_int, [i32, i32]),
     "ia2c_rollout": (C.c_int, [_DP, vp]),
     "ia2c_critic_phase": (C.c_int, [_DP, vp]),
     "ia2c_actor_phase": (C.c_int, [_DP, vp]),

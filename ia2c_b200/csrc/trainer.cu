@@ -7,16 +7,18 @@
 // generalised from 2 to N agents as specified in DESIGN.md ("Org-N"; identical to the reference at N=2).
 //
 // Kernels in this file
-//   rollout_step_kernel    one time step for all envs (general N): Org transition from act[t-1] (counts reduced by
-//                          warp shuffles, agents in lanes), observation, every agent's actor forward + sample ->
-//                          act[t], true-partner mode.  Per-agent actor weights staged in smem.  (N <= 8 uses the
-//                          persistent pipelined kernel of rollout_fused.cu instead.)
+//   env_step_kernel        one Org step for all envs (general N): action counts of step t-1 reduced by warp shuffles
+//                          (agents in lanes) -> true-partner mode, transition, reward, observation classes.
+//   actor_step_kernel      every agent's actor forward + sample -> act[t]; block = one agent x a strip of envs, the
+//                          agent's weights warp-uniform in registers (FFMA2).  (N <= 8 uses the persistent pipelined
+//                          kernel of rollout_fused.cu instead of these two.)
 //   critic_grad_kernel     a thread walks a time chunk of one (agent, env): ONE critic forward and ONE backward per
 //                          observation (TD target with gradient through both passes: residual gradient, SURVEY.md
 //                          Q8), FFMA2 math, accumulators in registers, block-reduced to partials (fixed order).
 //                          Skipped when the fused rollout already produced the critic partials.
 //   actor_grad_kernel      same walk: advantage from the updated critic, actor forward, Categorical
-//                          log-prob/entropy loss, closed-form backward, partials.
+//                          log-prob/entropy loss, closed-form backward, partials.  (Many-agent configs use the
+//                          warp-specialised actor_pipe_kernel of actor_pipe.cu; IA2C_FLAG_ACTOR_COLUMNS selects.)
 //   reduce_adam_kernel     sums the partials, writes grad (+loss), applies Adam (actor: accumulating gradient
 //                          buffer).
 //   allreduce_adam_kernel  multi-GPU: the same plus the gradient exchange over NVLink peer memory, in one kernel.
@@ -61,13 +63,12 @@ struct StepArgs {
 
 __device__ __forceinline__ uint32_t pack_count(int a) { return a == 0 ? 1u : (a == 1 ? (1u << 10) : (1u << 20)); }
 
-__global__ void __launch_bounds__(kRolloutThreads) rollout_step_kernel(StepArgs S) {
-    extern __shared__ float w_actor[];  // [N][105]
+// env_step_kernel, step t in 0..T+1: G lanes per env.  t == 0 resets; 1 <= t <= T counts the actions of step t-1
+// (agents strided over the group's lanes, counts reduced by shuffles), writes partner_true[t-1] (mode of the OTHERS'
+// actions) and advances the env; t == T+1 only writes partner_true[T].
+__global__ void __launch_bounds__(kRolloutThreads) env_step_kernel(StepArgs S) {
     const ia2c_episode_desc& d = S.d;
     const int N = d.N, G = S.G, t = S.t;
-    for (int i = threadIdx.x; i < N * kActorP; i += blockDim.x) w_actor[i] = d.actor_params[i];
-    __syncthreads();
-
     const int lane = threadIdx.x & 31;
     const int sub = lane & (G - 1);
     const int epw = 32 / G;                                        // envs per warp
@@ -76,20 +77,28 @@ __global__ void __launch_bounds__(kRolloutThreads) rollout_step_kernel(StepArgs 
     const bool live = e < d.E;                                     // whole group shares this
     const int64_t E = d.E;
 
-    // ---- environment: reset at t == 0, otherwise one Org step from act[t-1]
     int prev_cls = 1, cur_cls = 1;
     if (t > 0) {
         uint32_t packed = 0;
+        const uint8_t* a_prev = d.act + ((int64_t)(t - 1) * E + (live ? e : 0)) * N;
         if (live) {
-            const uint8_t* a_prev = d.act + ((int64_t)(t - 1) * E + e) * N;
             for (int i = sub; i < N; i += G) packed += pack_count(a_prev[i]);
         }
         for (int off = G >> 1; off > 0; off >>= 1) packed += __shfl_xor_sync(0xffffffffu, packed, off);
+        const int c0 = packed & 1023, c1 = (packed >> 10) & 1023, c2 = (packed >> 20) & 1023;
+        if (live) {
+            uint8_t* pt = d.partner_true + ((int64_t)(t - 1) * E + e) * N;
+            for (int i = sub; i < N; i += G) {
+                const int a = a_prev[i];
+                pt[i] = (uint8_t)mode3(c0 - (a == 0), c1 - (a == 1), c2 - (a == 2));
+            }
+        }
+        if (t > d.T) return;
         if (live && sub == 0) {
             const int s = d.env_state[e];
             int s2;
             double base;
-            org_transition(s, packed & 1023, (packed >> 10) & 1023, (packed >> 20) & 1023, N, s2, base);
+            org_transition(s, c0, c1, c2, N, s2, base);
             double r = org_reward(base, d.env_hist[e]);
             prev_cls = d.env_cls[2 * e + 1];
             cur_cls = org_obs_class(s2);
@@ -116,44 +125,43 @@ __global__ void __launch_bounds__(kRolloutThreads) rollout_step_kernel(StepArgs 
     const int leader = lane & ~(G - 1);
     prev_cls = __shfl_sync(0xffffffffu, prev_cls, leader);
     cur_cls = __shfl_sync(0xffffffffu, cur_cls, leader);
-    float x[F];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        x[k] = (k == prev_cls) ? 1.f : 0.f;
-        x[3 + k] = (k == cur_cls) ? 1.f : 0.f;
-    }
     if (live && sub < F) {
-        for (int k = sub; k < F; k += G) d.obs[((int64_t)t * E + e) * F + k] = x[k];
+        for (int k = sub; k < F; k += G)
+            d.obs[((int64_t)t * E + e) * F + k] = (k < 3 ? k == prev_cls : k - 3 == cur_cls) ? 1.f : 0.f;
     }
+}
 
-    // ---- every agent's actor forward + sample; agents strided over the group's lanes
-    uint8_t* act_t = d.act + ((int64_t)t * E + e) * N;
-    uint32_t packed = 0;
-    for (int i = sub; i < N; i += G) {
-        if (!live) break;
+// actor_step_kernel, step t in 0..T: every agent's actor forward + sample (ac_nets.py:94-102).  Block = one agent
+// (blockIdx.y) x a strip of envs, lane = env: the agent's weights are warp-uniform and live in registers (FFMA2,
+// mlp_f2.cuh), each thread walks up to kActorEnvsPerThread envs.
+constexpr int kActorThreads = 256, kActorEnvsPerThread = 4;
+__global__ void __launch_bounds__(kActorThreads) actor_step_kernel(StepArgs S) {
+    const ia2c_episode_desc& d = S.d;
+    const int N = d.N, t = S.t, i = blockIdx.y;
+    const int64_t E = d.E;
+    RegNet<A> net;
+    if (!d.inj_actions) load_regnet<A>(net, d.actor_params + (int64_t)i * kActorP);
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < E; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = ((int64_t)t * E + e) * N + i;
         int a;
         if (d.inj_actions) {
-            a = d.inj_actions[((int64_t)t * E + e) * N + i];
+            a = d.inj_actions[row];
         } else {
-            float h1[H], h2[H], y[A];
-            mlp_forward<F, A>(w_actor + i * kActorP, x, h1, h2, y);
+            const uchar2 cls = *reinterpret_cast<const uchar2*>(d.env_cls + 2 * e);
+            float x[F], y[A];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                x[k] = (k == cls.x) ? 1.f : 0.f;
+                x[3 + k] = (k == cls.y) ? 1.f : 0.f;
+            }
+            forward_regnet<A>(net, x, y);
             softmax_inplace<A>(y);
-            const float u = d.inj_u_action ? d.inj_u_action[((int64_t)t * E + e) * N + i]
+            const float u = d.inj_u_action ? d.inj_u_action[row]
                                            : philox_uniform_f32(d.seed, kStreamAction, d.episode, (uint32_t)t,
                                                                 (uint64_t)((d.env_offset + e) * N + i));
             a = sample_inverse_cdf<A>(y, u);
         }
-        act_t[i] = (uint8_t)a;
-        packed += pack_count(a);
-    }
-    for (int off = G >> 1; off > 0; off >>= 1) packed += __shfl_xor_sync(0xffffffffu, packed, off);
-    if (live) {
-        const int c0 = packed & 1023, c1 = (packed >> 10) & 1023, c2 = (packed >> 20) & 1023;
-        uint8_t* pt = d.partner_true + ((int64_t)t * E + e) * N;
-        for (int i = sub; i < N; i += G) {
-            const int a = act_t[i];  // written by this same thread above
-            pt[i] = (uint8_t)mode3(c0 - (a == 0), c1 - (a == 1), c2 - (a == 2));
-        }
+        d.act[row] = (uint8_t)a;
     }
 }
 
@@ -456,6 +464,8 @@ extern "C" size_t ia2c_episode_partials_floats(const ia2c_episode_desc* d) {
     return (size_t)d->N * blocks * (kCriticP + 1);
 }
 
+extern "C" int ia2c_rollout_fused_supported(int32_t N, int32_t M) { return rollout_fused_supported(N, M); }
+
 extern "C" int ia2c_rollout(const ia2c_episode_desc* d, void* stream) {
     if (int rc = validate(d, "ia2c_rollout")) return rc;
     IA2C_REQUIRE(d->env_state && d->env_hist && d->env_cls && d->env_elapsed && d->ep_return && d->belief_records &&
@@ -477,16 +487,17 @@ extern "C" int ia2c_rollout(const ia2c_episode_desc* d, void* stream) {
     const int epw = 32 / G;
     const int64_t warps = (d->E + epw - 1) / epw;
     const int blocks = ceil_div(warps * 32, kRolloutThreads);
-    const size_t smem = (size_t)d->N * kActorP * sizeof(float);
-    if (smem > 48 * 1024) {
-        IA2C_REQUIRE(smem <= 220 * 1024, "ia2c_rollout: N=%d actor weights do not fit shared memory", d->N);
-        cudaFuncSetAttribute(rollout_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    }
+    // up to kActorEnvsPerThread envs per thread (amortises the weight load) once that still leaves two waves of blocks
+    const int64_t ept = std::max<int64_t>(1, std::min<int64_t>(kActorEnvsPerThread, d->E * d->N / ((int64_t)kActorThreads * 2 * kSMs)));
+    dim3 actor_grid((unsigned)ceil_div(d->E, (int64_t)kActorThreads * ept), (unsigned)d->N);
     const int64_t EN = d->E * d->N, K = d->N - 1;
-    for (int t = 0; t <= d->T; ++t) {
+    for (int t = 0; t <= d->T + 1; ++t) {
         S.t = t;
-        rollout_step_kernel<<<blocks, kRolloutThreads, smem, s>>>(S);
-        if (int rc = check_launch("rollout_step_kernel")) return rc;
+        env_step_kernel<<<blocks, kRolloutThreads, 0, s>>>(S);
+        if (int rc = check_launch("env_step_kernel")) return rc;
+        if (t > d->T) break;   // the last call only completes partner_true[T]
+        actor_step_kernel<<<actor_grid, kActorThreads, 0, s>>>(S);
+        if (int rc = check_launch("actor_step_kernel")) return rc;
         int rc = ia2c_belief_update_pairs(
             d->belief_records, d->filter_action, d->act + (int64_t)t * EN,
             d->inj_u_belief ? d->inj_u_belief + (int64_t)t * EN * K : nullptr,

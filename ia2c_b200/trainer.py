@@ -49,7 +49,7 @@ def reference_init(n_agents, n_models, seed=None):
 class IA2CTrainer:
     def __init__(self, num_envs, n_agents=2, n_models=5, steps_per_episode=30, max_episode_steps=30,
                  lr_critic=0.0002, lr_actor=0.0001, beta=0.001, gamma=0.9, seed=0, device=None,
-                 rank=0, world_size=1, process_group=None, dumps=False, fused_rollout=False, fused_critic=None,
+                 rank=0, world_size=1, process_group=None, dumps=False, fused_rollout=None, fused_critic=None,
                  init=None, comm="auto", actor_kernel="auto"):
         _lib.require_cuda()
         if actor_kernel not in ("auto", "pipe", "columns"):
@@ -101,6 +101,8 @@ class IA2CTrainer:
         d.N, d.T, d.M, d.max_episode_steps = N, T, M, int(max_episode_steps or 0)
         d.gamma, d.beta, d.lr_actor, d.lr_critic = gamma, beta, lr_actor, lr_critic
         d.seed, d.episode = self.seed, 0
+        if fused_rollout is None:   # the persistent one-launch rollout wherever it has an instantiation
+            fused_rollout = bool(self.lib.ia2c_rollout_fused_supported(N, M))
         if fused_critic is None:
             fused_critic = bool(fused_rollout)   # the critic-gradient stage rides along with the fused rollout
         d.flags = ((_lib.FLAG_FUSED_ROLLOUT if fused_rollout else 0) | (_lib.FLAG_SKIP_ADAM if self.world > 1 else 0) |

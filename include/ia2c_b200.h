@@ -218,6 +218,9 @@ typedef struct ia2c_episode_desc {
 
 size_t ia2c_episode_partials_floats(const ia2c_episode_desc* d);
 
+/* 1 if IA2C_FLAG_FUSED_ROLLOUT has an instantiation for N agents and M models (N <= 8 with M = 5; N = 2 with M = 3). */
+int ia2c_rollout_fused_supported(int32_t N, int32_t M);
+
 /* Rollout only: ia2c.py:72-102 for all E envs (T+1 actor/belief evaluations, T env steps). */
 int ia2c_rollout(const ia2c_episode_desc* d, void* stream);
 /* Critic phase (ia2c.py:104-114): fused forward(obs) + forward(next_obs) + MSE + backward through
