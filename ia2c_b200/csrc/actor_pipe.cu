@@ -44,6 +44,7 @@ __global__ void __launch_bounds__(kPipeBlock) actor_pipe_kernel(ia2c_episode_des
     __shared__ float ql_s[4][2 * A][W];         // normalised probs q[0..A) | clamped logits [A..2A) (slot t & 3)
     __shared__ float2 dz1_s[2][3][W];           // dL/dz1 of row t                                  (slot t & 1)
 
+    pdl_prologue();
     const int role = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n = blockIdx.y, N = d.N, T = d.T;
     const int64_t E = d.E;
@@ -124,10 +125,7 @@ __global__ void __launch_bounds__(kPipeBlock) actor_pipe_kernel(ia2c_episode_des
 #pragma unroll
             for (int k = 0; k < 21; ++k) { out[2 * k] = gB[k].x; out[2 * k + 1] = gB[k].y; }
         }
-        return;
-    }
-
-    if (role == 1) {
+    } else if (role == 1) {
         // ================================================================ Cv: UPDATED critic forward, observation t = it-1
         RegNet<J> cnet;
         load_regnet<J>(cnet, d.critic_params + (int64_t)n * kCriticP);
@@ -147,10 +145,7 @@ __global__ void __launch_bounds__(kPipeBlock) actor_pipe_kernel(ia2c_episode_des
             }
             __syncthreads();
         }
-        return;
-    }
-
-    if (role == 2) {
+    } else if (role == 2) {
         // ================================================================ Pf: actor forward + Categorical(probs), observation t = it-1
         RegNet<A> anet;
         load_regnet<A>(anet, d.actor_params + (int64_t)n * kActorP);
@@ -182,9 +177,7 @@ __global__ void __launch_bounds__(kPipeBlock) actor_pipe_kernel(ia2c_episode_des
             }
             __syncthreads();
         }
-        return;
-    }
-
+    } else {
     // ==================================================================== Lb: advantage, loss, backward, row t = it-3
     constexpr int GA = F2<A>::G2 - 21;           // float2 accumulators for flat entries [42, 106): W2 | b2 | W3 | b3 | loss slot
     RegBack<A> back;
@@ -256,6 +249,7 @@ __global__ void __launch_bounds__(kPipeBlock) actor_pipe_kernel(ia2c_episode_des
         }
         out[P] = loss;
     }
+    }
 }
 
 }  // namespace
@@ -268,9 +262,8 @@ int64_t actor_pipe_blocks(int64_t E, int N) { const int w = 32 * pipe_columns(E,
 
 int actor_pipe_launch(const ia2c_episode_desc* d, cudaStream_t s) {
     dim3 grid((unsigned)actor_pipe_blocks(d->E, d->N), (unsigned)d->N);
-    if (pipe_columns(d->E, d->N) == 2) actor_pipe_kernel<2><<<grid, kPipeBlock, 0, s>>>(*d, d->partials);
-    else actor_pipe_kernel<1><<<grid, kPipeBlock, 0, s>>>(*d, d->partials);
-    return check_launch("actor_pipe_kernel");
+    if (pipe_columns(d->E, d->N) == 2) return launch_pdl("actor_pipe_kernel", actor_pipe_kernel<2>, grid, dim3(kPipeBlock), 0, s, *d, d->partials);
+    return launch_pdl("actor_pipe_kernel", actor_pipe_kernel<1>, grid, dim3(kPipeBlock), 0, s, *d, d->partials);
 }
 
 }  // namespace ia2c

@@ -160,6 +160,7 @@ __global__ void __launch_bounds__(kThreads) belief_pairs_kernel(PairsArgs P) {
     const int n_agents = i1 - i0;
     const int n_envs = (int)min((int64_t)P.envs_per_block, P.E - e0);
 
+    pdl_prologue();
     double* tab = reinterpret_cast<double*>(smem_raw);             // [101] k/100
     double* fa = tab + 104;                                        // [n_agents][M*A]
     int* counts = reinterpret_cast<int*>(fa + P.agents_per_block * M * A);   // [envs_per_block][agents_per_block][A]
@@ -269,13 +270,15 @@ __global__ void __launch_bounds__(kThreads, 4) belief_pairs_table_kernel(PairsAr
     float* fa32 = reinterpret_cast<float*>(fa + M * A);             // [M][A]
     int* counts = reinterpret_cast<int*>(fa32 + ((M * A + 3) & ~3)); // [EC][A]
     uint8_t* act = reinterpret_cast<uint8_t*>(counts + EC * A);     // [EC][N]
+    pdl_release();
+    // the table depends only on the agent's models: it is built while the kernel that samples this step's actions
+    // may still be running (programmatic dependent launch); pdl_wait() below orders the reads of its output
     for (int k = threadIdx.x; k <= 100; k += blockDim.x) tab[k] = __ddiv_rn((double)k, 100.0);
     for (int k = threadIdx.x; k < M * A; k += blockDim.x) {
         fa[k] = P.filter_action[(int64_t)i * M * A + k];
         fa32[k] = (float)fa[k];
     }
     for (int k = threadIdx.x; k < n_envs * A; k += blockDim.x) counts[k] = 0;
-    for (int k = threadIdx.x; k < n_envs * N; k += blockDim.x) act[k] = P.actions[e0 * N + k];
     __syncthreads();
     for (int x = threadIdx.x; x < A * M * 101; x += blockDim.x) {
         const int seen = x / (M * 101), m = (x / 101) % M, k = x % 101;
@@ -285,6 +288,8 @@ __global__ void __launch_bounds__(kThreads, 4) belief_pairs_table_kernel(PairsAr
         for (int a = 1; a < A; ++a) acc = __dadd_rn(acc, __dmul_rn(seen == a ? 0.8 : 0.1, __dmul_rn(fa[m * A + a], p)));
         bpt[x] = acc;
     }
+    pdl_wait();
+    for (int k = threadIdx.x; k < n_envs * N; k += blockDim.x) act[k] = P.actions[e0 * N + k];
     __syncthreads();
     const int prior_k = (int)rint(100.0 / M);
     // One thread = one PAIR of modelled-other slots (2s, 2s+1) of one env: the two records share a Philox block and
@@ -428,12 +433,11 @@ int launch_pairs_table(PairsArgs& P, cudaStream_t stream) {
     const bool fast = !P.reset_prior && !P.u_injected && !P.belief_out && !P.pred_out && P.pred_partner_out;
     if (fast) {
         if (smem > 48 * 1024) cudaFuncSetAttribute(belief_pairs_table_kernel<M, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        belief_pairs_table_kernel<M, true><<<grid, kThreads, smem, stream>>>(P);
+        return launch_pdl("belief_pairs_table_kernel", belief_pairs_table_kernel<M, true>, grid, dim3(kThreads), smem, stream, P);
     } else {
         if (smem > 48 * 1024) cudaFuncSetAttribute(belief_pairs_table_kernel<M, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        belief_pairs_table_kernel<M, false><<<grid, kThreads, smem, stream>>>(P);
+        return launch_pdl("belief_pairs_table_kernel", belief_pairs_table_kernel<M, false>, grid, dim3(kThreads), smem, stream, P);
     }
-    return check_launch("belief_pairs_table_kernel");
 }
 
 template <int M>
@@ -460,8 +464,7 @@ int launch_pairs(PairsArgs& P, cudaStream_t stream) {
     if (smem > 48 * 1024) {
         cudaFuncSetAttribute(belief_pairs_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     }
-    belief_pairs_kernel<M><<<(unsigned)blocks, kThreads, smem, stream>>>(P);
-    return check_launch("belief_pairs_kernel");
+    return launch_pdl("belief_pairs_kernel", belief_pairs_kernel<M>, dim3((unsigned)blocks), dim3(kThreads), smem, stream, P);
 }
 
 }  // namespace

@@ -71,6 +71,7 @@ __global__ void __launch_bounds__(kBlock) rollout_fused_kernel(ia2c_episode_desc
     __shared__ float2 hst_s[4][6][CRITIC ? 32 : 1];      // critic activations (h1 | h2 pairs) of obs[t], slot t & 3
     __shared__ float2 dz1_s[2][3][CRITIC ? 32 : 1];      // dL/dz1 of observation t (backprop warp -> W1-gradient owner), slot t & 1
     __shared__ float4 dy_s[4][CRITIC ? 32 : 1];          // row t's output gradients {jt, dQ[jt], nja, dQ'[nja]}, slot t & 3
+    pdl_prologue();
     for (int k = threadIdx.x; k <= 100; k += blockDim.x) tab[k] = __ddiv_rn((double)k, 100.0);
     for (int k = threadIdx.x; k < N * M * A; k += blockDim.x) fa_s[k] = d.filter_action[k];
     __syncthreads();
@@ -203,10 +204,7 @@ __global__ void __launch_bounds__(kBlock) rollout_fused_kernel(ia2c_episode_desc
             d.ep_return[e] = ep_ret;
             *reinterpret_cast<uchar2*>(d.env_cls + 2 * e) = make_uchar2((unsigned char)prev_cls, (unsigned char)cur_cls);
         }
-        return;
-    }
-
-    if (role == 2) {
+    } else if (role == 2) {
         // ================================================================ B: beliefs, step t = it - 2
         const double* fa = fa_s + i * M * A;
         int bel[K][M];
@@ -293,17 +291,14 @@ __global__ void __launch_bounds__(kBlock) rollout_fused_kernel(ia2c_episode_desc
                 *reinterpret_cast<uint2*>(d.belief_records + ((e * N + i) * (int64_t)K + jj) * IA2C_BELIEF_RECORD) = make_uint2(lo, hi);
             }
         }
-        return;
-    }
-
-    // ==================================================================== R + Cf / Cb: draws, critic gradient
-    if (!CRITIC) {
+    } else if (!CRITIC) {
+        // ================================================================ R alone: draws (no critic stage)
         for (int it = 0; it < n_iter; ++it) {
             if (role == 3) draw_step(it);
             __syncthreads();
         }
-        return;
-    }
+    } else {
+    // ==================================================================== R + Cf / Cb: draws, critic gradient
     constexpr int P = kCriticP, GN = F2<J>::G2;          // 148 floats = 74 float2 (147 gradient entries + the loss)
     const float inv_b = agent ? 1.f / (float)((int64_t)T * d.E_total) : 0.f;   // dead lanes contribute nothing
     float* out = partials + ((int64_t)(lane < N ? lane : 0) * gridDim.x + blockIdx.x) * (P + 1);
@@ -387,9 +382,7 @@ __global__ void __launch_bounds__(kBlock) rollout_fused_kernel(ia2c_episode_desc
             out[P] = loss;
             if (blockIdx.x == 0 && !(d.flags & IA2C_FLAG_SKIP_ADAM)) d.critic_step[lane] += 1;
         }
-        return;
-    }
-
+    } else {
     // ==================================================================== Cb: critic backward, observation t = it - 5
     // ONE backward per observation with both output-gradient contributions it receives (from row t as
     // Q(obs_t)[jt_t], from row t-1 as the bootstrap Q(next_obs_{t-1})[nja_{t-1}]); 147 gradient accumulators
@@ -441,6 +434,8 @@ __global__ void __launch_bounds__(kBlock) rollout_fused_kernel(ia2c_episode_desc
             if (42 + 2 * k + 1 < P) out[42 + 2 * k + 1] = gA[k].y;
         }
     }
+    }   // Cb
+    }   // critic stages
 }
 
 template <int N, int M>
@@ -448,10 +443,8 @@ int launch(const ia2c_episode_desc* d, cudaStream_t s) {
     constexpr int G = N <= 2 ? 2 : (N <= 4 ? 4 : 8);
     const int64_t blocks = (d->E + (32 / G) - 1) / (32 / G);   // one block = 4 stage warps over 32/G envs
     if (d->flags & IA2C_FLAG_FUSED_CRITIC)
-        rollout_fused_kernel<N, M, true><<<(unsigned)blocks, kBlock, 0, s>>>(*d, d->partials);
-    else
-        rollout_fused_kernel<N, M, false><<<(unsigned)blocks, kBlock, 0, s>>>(*d, nullptr);
-    return check_launch("rollout_fused_kernel");
+        return launch_pdl("rollout_fused_kernel", rollout_fused_kernel<N, M, true>, dim3((unsigned)blocks), dim3(kBlock), 0, s, *d, d->partials);
+    return launch_pdl("rollout_fused_kernel", rollout_fused_kernel<N, M, false>, dim3((unsigned)blocks), dim3(kBlock), 0, s, *d, nullptr);
 }
 
 }  // namespace

@@ -27,6 +27,7 @@
 
 #include "common.cuh"
 #include "mlp_f2.cuh"
+#include "reduce.cuh"
 
 namespace ia2c {
 int rollout_fused_supported(int N, int M);                                  // rollout_fused.cu
@@ -67,6 +68,7 @@ __device__ __forceinline__ uint32_t pack_count(int a) { return a == 0 ? 1u : (a 
 // (agents strided over the group's lanes, counts reduced by shuffles), writes partner_true[t-1] (mode of the OTHERS'
 // actions) and advances the env; t == T+1 only writes partner_true[T].
 __global__ void __launch_bounds__(kRolloutThreads) env_step_kernel(StepArgs S) {
+    pdl_prologue();
     const ia2c_episode_desc& d = S.d;
     const int N = d.N, G = S.G, t = S.t;
     const int lane = threadIdx.x & 31;
@@ -136,6 +138,7 @@ __global__ void __launch_bounds__(kRolloutThreads) env_step_kernel(StepArgs S) {
 // mlp_f2.cuh), each thread walks up to kActorEnvsPerThread envs.
 constexpr int kActorThreads = 256, kActorEnvsPerThread = 4;
 __global__ void __launch_bounds__(kActorThreads) actor_step_kernel(StepArgs S) {
+    pdl_prologue();
     const ia2c_episode_desc& d = S.d;
     const int N = d.N, t = S.t, i = blockIdx.y;
     const int64_t E = d.E;
@@ -195,6 +198,7 @@ __global__ void __launch_bounds__(kGradThreads) critic_grad_kernel(ia2c_episode_
     constexpr int P = kCriticP, GN = F2<J>::G2;   // 148 floats = 74 float2
     __shared__ __align__(16) float w[SmemNet<J>::size];
     __shared__ float red[(kGradThreads / 32) * (P + 1)];
+    pdl_prologue();
     const int n = blockIdx.y, N = d.N;
     stage_smemnet<J>(w, d.critic_params + (int64_t)n * P);
     if (blockIdx.x == 0 && threadIdx.x == 0 && !(d.flags & IA2C_FLAG_SKIP_ADAM)) d.critic_step[n] += 1;
@@ -254,6 +258,7 @@ __global__ void __launch_bounds__(kGradThreads) actor_grad_kernel(ia2c_episode_d
     __shared__ __align__(16) float wc[SmemNet<J>::size];
     __shared__ __align__(16) float w[SmemNet<A>::size];
     __shared__ float red[(kGradThreads / 32) * (P + 1)];
+    pdl_prologue();
     const int n = blockIdx.y, N = d.N;
     stage_smemnet<J>(wc, d.critic_params + (int64_t)n * PC);
     stage_smemnet<A>(w, d.actor_params + (int64_t)n * P);
@@ -331,36 +336,13 @@ __global__ void __launch_bounds__(kGradThreads) actor_grad_kernel(ia2c_episode_d
     block_reduce_store<P + 1>(reinterpret_cast<float(&)[P + 1]>(g), red, partials + ((int64_t)n * gridDim.x + blockIdx.x) * (P + 1));
 }
 
-// Sum partials over blocks (fixed order) -> grad[n][0..P] (slot P = loss); optionally Adam.
-struct ReduceArgs {
-    const float* partials;
-    int n_blocks, P;
-    float* grad;            // [N, P+1]
-    float* grad_accum;      // [N, P] or null
-    float* params; float* m; float* v;
-    int32_t* step;          // [N], already incremented for this update
-    float* loss_out;        // [N]
-    float loss_scale;       // 1 / (T * E_total)
-    double lr;
-    int apply_adam, from_partials;
-};
-
-__device__ __forceinline__ void adam_update(float& p, float& m, float& v, float g, int t, double lr) {
-    const double b1 = 0.9, b2 = 0.999;
-    const double bc1 = 1.0 - pow(b1, (double)t), bc2 = 1.0 - pow(b2, (double)t);
-    const float step_size = (float)(lr / bc1), bc2_sqrt = (float)sqrt(bc2);
-    const float mi = m + (g - m) * (float)(1.0 - b1);
-    const float vi = v * (float)b2 + (float)(1.0 - b2) * g * g;
-    m = mi;
-    v = vi;
-    p = p - step_size * (mi / (sqrtf(vi) / bc2_sqrt + 1e-8f));
-}
-
+// Sum partials over blocks (fixed order) -> grad[n][0..P] (slot P = loss); optionally Adam.  (reduce.cuh holds
+// ReduceArgs and the per-entry epilogue with the Adam step.)
 // grid (N, ceil((P+1)/32)); block 1024 = 32 entries x 32 slices of the partial blocks; fixed-order sums.
 // The partials are L2-resident, so a thread's chain of dependent adds costs one L2 round trip per term: many
 // short slices (<= 8 terms at 256 partial blocks, loads issued back to back) instead of few long ones.
-constexpr int kReduceSlices = 32;
 __global__ void __launch_bounds__(32 * kReduceSlices) reduce_adam_kernel(ReduceArgs R) {
+    pdl_prologue();
     const int n = blockIdx.x, P = R.P;
     const int col = threadIdx.x & 31, slice = threadIdx.x >> 5;
     const int i = blockIdx.y * 32 + col;
@@ -388,22 +370,7 @@ __global__ void __launch_bounds__(32 * kReduceSlices) reduce_adam_kernel(ReduceA
     if (slice != 0 || i > P) return;
 #pragma unroll
     for (int k = 1; k < kReduceSlices; ++k) s += part[k][col];
-    if (R.from_partials) {
-        if (i == P) s *= R.loss_scale;
-        R.grad[(int64_t)n * (P + 1) + i] = s;
-    }
-    if (i == P) {
-        R.loss_out[n] = s;
-    } else if (R.apply_adam) {
-        const int t = R.step[n];             // already incremented by the gradient kernel / apply entry
-        const int64_t k = (int64_t)n * P + i;
-        float g = s;
-        if (R.grad_accum) {                  // the reference's actor never zeroes its gradients (Q2)
-            g += R.grad_accum[k];
-            R.grad_accum[k] = g;
-        }
-        adam_update(R.params[k], R.m[k], R.v[k], g, t, R.lr);
-    }
+    finish_entry(R, n, i, s);
 }
 
 __global__ void bump_steps_kernel(int32_t* step, int n) {
@@ -453,8 +420,7 @@ static int actor_partial_blocks(const ia2c_episode_desc* d) {
 static int launch_actor_grad(const ia2c_episode_desc* d, cudaStream_t s) {
     if (!actor_columns(d)) return actor_pipe_launch(d, s);
     dim3 grid(grad_blocks(d), d->N);
-    actor_grad_kernel<<<grid, kGradThreads, 0, s>>>(*d, d->partials);
-    return check_launch("actor_grad_kernel");
+    return launch_pdl("actor_grad_kernel", actor_grad_kernel, grid, dim3(kGradThreads), 0, s, *d, d->partials);
 }
 
 extern "C" size_t ia2c_episode_partials_floats(const ia2c_episode_desc* d) {
@@ -493,11 +459,9 @@ extern "C" int ia2c_rollout(const ia2c_episode_desc* d, void* stream) {
     const int64_t EN = d->E * d->N, K = d->N - 1;
     for (int t = 0; t <= d->T + 1; ++t) {
         S.t = t;
-        env_step_kernel<<<blocks, kRolloutThreads, 0, s>>>(S);
-        if (int rc = check_launch("env_step_kernel")) return rc;
+        if (int rc = launch_pdl("env_step_kernel", env_step_kernel, dim3(blocks), dim3(kRolloutThreads), 0, s, S)) return rc;
         if (t > d->T) break;   // the last call only completes partner_true[T]
-        actor_step_kernel<<<actor_grid, kActorThreads, 0, s>>>(S);
-        if (int rc = check_launch("actor_step_kernel")) return rc;
+        if (int rc = launch_pdl("actor_step_kernel", actor_step_kernel, actor_grid, dim3(kActorThreads), 0, s, S)) return rc;
         int rc = ia2c_belief_update_pairs(
             d->belief_records, d->filter_action, d->act + (int64_t)t * EN,
             d->inj_u_belief ? d->inj_u_belief + (int64_t)t * EN * K : nullptr,
@@ -511,19 +475,7 @@ extern "C" int ia2c_rollout(const ia2c_episode_desc* d, void* stream) {
 }
 
 static int run_reduce(const ia2c_episode_desc* d, int which, int from_partials, int apply, cudaStream_t s) {
-    ReduceArgs R;
-    R.partials = d->partials;
-    R.n_blocks = which == 0 ? critic_partial_blocks(d) : actor_partial_blocks(d);
-    R.P = which == 0 ? kCriticP : kActorP;
-    R.grad = which == 0 ? d->critic_grad : d->actor_grad;
-    R.grad_accum = which == 0 ? nullptr : d->actor_grad_accum;
-    R.params = which == 0 ? d->critic_params : d->actor_params;
-    R.m = which == 0 ? d->critic_m : d->actor_m;
-    R.v = which == 0 ? d->critic_v : d->actor_v;
-    R.step = which == 0 ? d->critic_step : d->actor_step;
-    R.loss_out = d->loss_out + (which == 0 ? 0 : d->N);
-    R.loss_scale = 1.f / (float)((int64_t)d->T * d->E_total);
-    R.lr = which == 0 ? d->lr_critic : d->lr_actor;
+    ReduceArgs R = make_reduce_args(*d, which, which == 0 ? critic_partial_blocks(d) : actor_partial_blocks(d));
     R.apply_adam = apply;
     R.from_partials = from_partials;
     if (!from_partials && apply) {   // ia2c_apply_adam: the gradient kernel did not bump the step counter
@@ -531,8 +483,7 @@ static int run_reduce(const ia2c_episode_desc* d, int which, int from_partials, 
         if (int rc = check_launch("bump_steps_kernel")) return rc;
     }
     dim3 grid(d->N, ceil_div(R.P + 1, 32));
-    reduce_adam_kernel<<<grid, 32 * kReduceSlices, 0, s>>>(R);
-    return check_launch("reduce_adam_kernel");
+    return launch_pdl("reduce_adam_kernel", reduce_adam_kernel, grid, dim3(32 * kReduceSlices), 0, s, R);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -653,8 +604,7 @@ extern "C" int ia2c_critic_phase(const ia2c_episode_desc* d, void* stream) {
     cudaStream_t s = as_stream(stream);
     if (!fused_critic(d)) {   // otherwise the rollout kernel's critic stage already wrote the partials
         dim3 grid(grad_blocks(d), d->N);
-        critic_grad_kernel<<<grid, kGradThreads, 0, s>>>(*d, d->partials);
-        if (int rc = check_launch("critic_grad_kernel")) return rc;
+        if (int rc = launch_pdl("critic_grad_kernel", critic_grad_kernel, grid, dim3(kGradThreads), 0, s, *d, d->partials)) return rc;
     }
     if (d->flags & IA2C_FLAG_GRAD_ONLY) return 0;
     return run_reduce(d, 0, 1, !(d->flags & IA2C_FLAG_SKIP_ADAM), s);

@@ -238,8 +238,13 @@ class IA2CTrainer:
 
     def train_episode(self, sync_stats=False):
         """One episode: rollout, critic update, actor update.  Asynchronous unless ``sync_stats``."""
-        self.rollout()
-        self.update()
+        if self.world == 1:   # one C call for the whole episode
+            self.desc.episode = self.episode
+            with torch.cuda.device(self.device):
+                _lib.check(self.lib.ia2c_train_episode(C.byref(self.desc), self._stream()), "ia2c_train_episode")
+        else:
+            self.rollout()
+            self.update()
         self.episode += 1
         if sync_stats:
             return self.read_stats()

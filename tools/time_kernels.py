@@ -17,5 +17,19 @@ for (E, N, fused, fc, ak) in configs:
     for _ in range(n):
         for k, v in tr.train_episode_timed().items():
             acc[k] = acc.get(k, 0) + v / n
+    import torch
+    for _once in (0,):
+        t2 = IA2CTrainer(E, n_agents=N, init=reference_init(N, 5, seed=0), seed=7, fused_rollout=fused, fused_critic=fc,
+                         actor_kernel=ak)
+        for _ in range(5):
+            t2.train_episode()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a.record()
+        for _ in range(50):
+            t2.train_episode()
+        b.record()
+        torch.cuda.synchronize()
+        print(f"   back-to-back episodes: {a.elapsed_time(b) / 50 * 1000:.1f} us")
     print(f"E={E} N={N} fused_rollout={fused} fused_critic={fc} actor={ak}", {k: round(v * 1000, 2) for k, v in acc.items()}, "us",
           "total", round(sum(acc.values()) * 1000, 1))
