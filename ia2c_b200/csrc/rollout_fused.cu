@@ -71,10 +71,12 @@ __global__ void __launch_bounds__(kBlock) rollout_fused_kernel(ia2c_episode_desc
     __shared__ float2 hst_s[4][6][CRITIC ? 32 : 1];      // critic activations (h1 | h2 pairs) of obs[t], slot t & 3
     __shared__ float2 dz1_s[2][3][CRITIC ? 32 : 1];      // dL/dz1 of observation t (backprop warp -> W1-gradient owner), slot t & 1
     __shared__ float4 dy_s[4][CRITIC ? 32 : 1];          // row t's output gradients {jt, dQ[jt], nja, dQ'[nja]}, slot t & 3
-    pdl_prologue();
+    pdl_release();
+    // constants of the run (k/100, the agents' models): staged while the previous kernel of the stream may still be running
     for (int k = threadIdx.x; k <= 100; k += blockDim.x) tab[k] = __ddiv_rn((double)k, 100.0);
     for (int k = threadIdx.x; k < N * M * A; k += blockDim.x) fa_s[k] = d.filter_action[k];
     __syncthreads();
+    pdl_wait();   // parameters (updated by the previous episode's Adam steps) are read only after this
 
     const int role = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
