@@ -515,6 +515,7 @@ __global__ void __launch_bounds__(32 * kReduceSlices) allreduce_adam_kernel(Redu
                                                                             int chunks_per_agent) {
     __shared__ float part[kReduceSlices][33];
     __shared__ int timeout;
+    pdl_prologue();
     const int P = R.P, col = threadIdx.x & 31, slice = threadIdx.x >> 5;
     const int parity = (int)(X.epoch & 1u);
     if (threadIdx.x == 0) timeout = 0;
@@ -815,6 +816,5 @@ extern "C" int ia2c_allreduce_adam(const ia2c_episode_desc* d, int32_t which, co
     phase_regions(d, peers->world, which, X.inbox_base, X.stride, X.flag_base, chunks_per_agent);
     const int total = d->N * chunks_per_agent;
     const int grid = std::min(total, kSMs);          // persistent: every block is resident
-    allreduce_adam_kernel<<<grid, 32 * kReduceSlices, 0, s>>>(R, X, total, chunks_per_agent);
-    return check_launch("allreduce_adam_kernel");
+    return launch_pdl("allreduce_adam_kernel", allreduce_adam_kernel, dim3(grid), dim3(32 * kReduceSlices), 0, s, R, X, total, chunks_per_agent);
 }
