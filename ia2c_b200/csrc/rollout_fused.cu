@@ -92,15 +92,31 @@ __global__ void __launch_bounds__(kBlock) rollout_fused_kernel(ia2c_episode_desc
 
     // ---- R: uniforms for step t (device Philox or the injected tapes) -> shared-memory rings.  Executed by warp 0
     //         at the top of each of its iterations (it shares the warp with the critic-forward stage).
-    auto draw_step = [&](int t) {
+    // Injected tapes are fetched TWO steps ahead into registers (freshly copied tapes sit in HBM: a load issued in the
+    // iteration that needs it would hold the whole block at the barrier for a DRAM round trip).
+    struct Tape { float ua; double ub[K]; } tp0, tp1;
+    const bool inj_a = d.inj_u_action != nullptr, inj_b = d.inj_u_belief != nullptr;
+    auto tape_fetch = [&](Tape& tp, int t) {
         if (t <= T && agent) {
             const int64_t row = ((int64_t)t * E + e) * N + i;
-            ua_s[t & 1][lane] = d.inj_u_action ? d.inj_u_action[row]
-                                               : philox_uniform_f32(d.seed, kStreamAction, d.episode, (uint32_t)t,
-                                                                    (uint64_t)((d.env_offset + e) * N + i));
-            if (d.inj_u_belief) {
+            if (inj_a) tp.ua = __ldg(d.inj_u_action + row);
+            if (inj_b) {
 #pragma unroll
-                for (int jj = 0; jj < K; ++jj) ub_s[t & 3][jj][lane] = d.inj_u_belief[row * K + jj];
+                for (int jj = 0; jj < K; ++jj) tp.ub[jj] = __ldg(d.inj_u_belief + row * K + jj);
+            }
+        }
+    };
+    auto draw_init = [&]() {
+        if (inj_a || inj_b) { tape_fetch(tp0, 0); tape_fetch(tp1, 1); }
+    };
+    auto draw_from = [&](Tape& tp, int t) {
+        if (t <= T && agent) {
+            ua_s[t & 1][lane] = inj_a ? tp.ua
+                                      : philox_uniform_f32(d.seed, kStreamAction, d.episode, (uint32_t)t,
+                                                           (uint64_t)((d.env_offset + e) * N + i));
+            if (inj_b) {
+#pragma unroll
+                for (int jj = 0; jj < K; ++jj) ub_s[t & 3][jj][lane] = tp.ub[jj];
             } else {
 #pragma unroll
                 for (int sl = 0; sl < (K + 1) / 2; ++sl) {
@@ -111,6 +127,10 @@ __global__ void __launch_bounds__(kBlock) rollout_fused_kernel(ia2c_episode_desc
                 }
             }
         }
+        if (inj_a || inj_b) tape_fetch(tp, t + 2);
+    };
+    auto draw_step = [&](int t) {
+        if (t & 1) draw_from(tp1, t); else draw_from(tp0, t);
     };
 
     if (role == 1) {
@@ -295,6 +315,7 @@ __global__ void __launch_bounds__(kBlock) rollout_fused_kernel(ia2c_episode_desc
         }
     } else if (!CRITIC) {
         // ================================================================ R alone: draws (no critic stage)
+        if (role == 3) draw_init();
         for (int it = 0; it < n_iter; ++it) {
             if (role == 3) draw_step(it);
             __syncthreads();
@@ -395,6 +416,7 @@ __global__ void __launch_bounds__(kBlock) rollout_fused_kernel(ia2c_episode_desc
     float2 gA[GA];
 #pragma unroll
     for (int k = 0; k < GA; ++k) gA[k] = make_float2(0.f, 0.f);
+    draw_init();
     for (int it = 0; it < n_iter; ++it) {
         draw_step(it);               // stage R shares this warp
         const int t = it - 5;

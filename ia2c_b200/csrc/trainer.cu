@@ -24,6 +24,8 @@
 //   allreduce_adam_kernel  multi-GPU: the same plus the gradient exchange over NVLink peer memory, in one kernel.
 // The belief update between steps is belief_pairs(_table)_kernel (belief.cu).
 #include <algorithm>
+#include <chrono>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "mlp_f2.cuh"
@@ -665,8 +667,9 @@ extern "C" int ia2c_train_episode_host(const ia2c_episode_desc* d, const float* 
 // episode's losses and returns are read back to its own host slot; one host sync at the end.
 namespace {
 struct HostPipe {
-    cudaStream_t copy = nullptr;
+    cudaStream_t copy = nullptr, down = nullptr;
     cudaEvent_t copied[2] = {nullptr, nullptr}, consumed[2] = {nullptr, nullptr};
+    cudaEvent_t done[2] = {nullptr, nullptr}, downloaded[2] = {nullptr, nullptr};
     int device = -1;
 };
 thread_local HostPipe g_pipe;
@@ -677,9 +680,10 @@ int pipe_init() {
     if (g_pipe.copy && g_pipe.device == dev) return 0;
     g_pipe.device = dev;
     if (cudaStreamCreateWithFlags(&g_pipe.copy, cudaStreamNonBlocking) != cudaSuccess) return check_launch("cudaStreamCreate");
+    if (cudaStreamCreateWithFlags(&g_pipe.down, cudaStreamNonBlocking) != cudaSuccess) return check_launch("cudaStreamCreate");
     for (int i = 0; i < 2; ++i) {
-        if (cudaEventCreateWithFlags(&g_pipe.copied[i], cudaEventDisableTiming) != cudaSuccess) return check_launch("cudaEventCreate");
-        if (cudaEventCreateWithFlags(&g_pipe.consumed[i], cudaEventDisableTiming) != cudaSuccess) return check_launch("cudaEventCreate");
+        for (cudaEvent_t* ev : {&g_pipe.copied[i], &g_pipe.consumed[i], &g_pipe.done[i], &g_pipe.downloaded[i]})
+            if (cudaEventCreateWithFlags(ev, cudaEventDisableTiming) != cudaSuccess) return check_launch("cudaEventCreate");
     }
     return 0;
 }
@@ -697,7 +701,7 @@ extern "C" size_t ia2c_host_result_bytes(const ia2c_episode_desc* d) {
     return align8(2 * (size_t)d->N * sizeof(float)) + (size_t)d->E * sizeof(double);
 }
 
-extern "C" int ia2c_train_episodes_host(const ia2c_episode_desc* d, void* stage_b, int32_t n_episodes,
+extern "C" int ia2c_train_episodes_host(const ia2c_episode_desc* d, void* stage_b, void* result_b, int32_t n_episodes,
                                         const void* const* host_tapes, void* host_results, void* stream) {
     if (int rc = validate(d, "ia2c_train_episodes_host")) return rc;
     IA2C_REQUIRE(!(d->flags & IA2C_FLAG_SKIP_ADAM), "ia2c_train_episodes_host: single-rank entry point (SKIP_ADAM set)");
@@ -713,10 +717,14 @@ extern "C" int ia2c_train_episodes_host(const ia2c_episode_desc* d, void* stage_
     if (int rc = pipe_init()) return rc;
     cudaStream_t s = as_stream(stream);
     char* stage[2] = {reinterpret_cast<char*>(const_cast<float*>(d->inj_u_action)), reinterpret_cast<char*>(stage_b)};
+    // with a second result region the D2H of episode k runs on its own stream while episode k+1 computes
+    char* result[2] = {reinterpret_cast<char*>(d->loss_out), result_b ? reinterpret_cast<char*>(result_b) : reinterpret_cast<char*>(d->loss_out)};
     // the copy stream must not overwrite a staging set that earlier work on `s` may still read
     if (cudaEventRecord(g_pipe.consumed[0], s) != cudaSuccess || cudaEventRecord(g_pipe.consumed[1], s) != cudaSuccess)
         return check_launch("cudaEventRecord");
     ia2c_episode_desc e = *d;
+    const bool trace = getenv("IA2C_TRACE_HOST") != nullptr;   // diagnostics: host enqueue time vs total
+    const auto t_begin = std::chrono::steady_clock::now();
     for (int k = 0; k < n_episodes; ++k) {
         const int b = k & 1;
         cudaStreamWaitEvent(g_pipe.copy, g_pipe.consumed[b], 0);
@@ -724,15 +732,38 @@ extern "C" int ia2c_train_episodes_host(const ia2c_episode_desc* d, void* stage_
             return check_launch("memcpy H2D uniforms");
         cudaEventRecord(g_pipe.copied[b], g_pipe.copy);
         cudaStreamWaitEvent(s, g_pipe.copied[b], 0);
+        if (result_b && k >= 2) cudaStreamWaitEvent(s, g_pipe.downloaded[b], 0);   // region b was read back before it is rewritten
         e.inj_u_action = reinterpret_cast<const float*>(stage[b]);
         e.inj_u_belief = reinterpret_cast<const double*>(stage[b] + off_b);
+        e.loss_out = reinterpret_cast<float*>(result[b]);
+        e.ep_return = reinterpret_cast<double*>(result[b] + off_ret);
         e.episode = d->episode + (uint32_t)k;
         if (int rc = ia2c_train_episode(&e, stream)) return rc;
         cudaEventRecord(g_pipe.consumed[b], s);
-        if (cudaMemcpyAsync(reinterpret_cast<char*>(host_results) + (size_t)k * res_bytes, d->loss_out, res_bytes, cudaMemcpyDeviceToHost, s) != cudaSuccess)
+        char* host_slot = reinterpret_cast<char*>(host_results) + (size_t)k * res_bytes;
+        if (result_b) {
+            cudaEventRecord(g_pipe.done[b], s);
+            cudaStreamWaitEvent(g_pipe.down, g_pipe.done[b], 0);
+            if (cudaMemcpyAsync(host_slot, result[b], res_bytes, cudaMemcpyDeviceToHost, g_pipe.down) != cudaSuccess)
+                return check_launch("memcpy D2H results");
+            cudaEventRecord(g_pipe.downloaded[b], g_pipe.down);
+        } else if (cudaMemcpyAsync(host_slot, result[0], res_bytes, cudaMemcpyDeviceToHost, s) != cudaSuccess) {
             return check_launch("memcpy D2H results");
+        }
     }
+    if (result_b && !(n_episodes & 1)) {   // leave the last episode's results in the descriptor's own region
+        if (cudaMemcpyAsync(result[0], result[1], res_bytes, cudaMemcpyDeviceToDevice, s) != cudaSuccess)
+            return check_launch("memcpy D2D results");
+    }
+    const auto t_enqueued = std::chrono::steady_clock::now();
     if (cudaStreamSynchronize(s) != cudaSuccess) return check_launch("stream sync");
+    if (result_b && cudaStreamSynchronize(g_pipe.down) != cudaSuccess) return check_launch("download stream sync");
+    if (trace) {
+        const auto t_done = std::chrono::steady_clock::now();
+        fprintf(stderr, "ia2c_train_episodes_host: %d episodes, enqueue %.1f us/episode, total %.1f us/episode\n", n_episodes,
+                std::chrono::duration<double, std::micro>(t_enqueued - t_begin).count() / n_episodes,
+                std::chrono::duration<double, std::micro>(t_done - t_begin).count() / n_episodes);
+    }
     return 0;
 }
 

@@ -296,7 +296,7 @@ class IA2CTrainer:
 
     def train_episodes_host(self, host_tapes):
         """Pipelined end-to-end form: a list of per-episode pinned host tapes (``pack_host_tape``) in, per-episode
-        losses and returns out.  One H2D copy per episode, overlapping the previous episode's compute, and one D2H
+        losses and returns out (the loss / return windows are updated; ``window_stats()`` computes their means on demand).  One H2D copy per episode, overlapping the previous episode's compute, and one D2H
         copy of the result region (``ia2c_train_episodes_host``; multi-rank: the same pipeline with torch streams)."""
         n = len(host_tapes)
         N, E = self.N, self.E
@@ -308,19 +308,26 @@ class IA2CTrainer:
             self._pipeline_multirank(host_tapes)
         else:
             ptrs = (C.c_void_p * n)(*[t.data_ptr() for t in host_tapes])
+            if getattr(self, "_result_region_b", None) is None:
+                self._result_region_b = torch.zeros_like(self._result_region)
             self.desc.episode = self.episode
             with torch.cuda.device(self.device):
-                _lib.check(self.lib.ia2c_train_episodes_host(C.byref(self.desc), self._stage[1].data_ptr(), n, ptrs,
+                _lib.check(self.lib.ia2c_train_episodes_host(C.byref(self.desc), self._stage[1].data_ptr(),
+                                                             self._result_region_b.data_ptr(), n, ptrs,
                                                              self._h_results.data_ptr(), self._stream()),
                            "ia2c_train_episodes_host")
             self.episode += n
-        out = []
-        for k in range(n):
-            row = self._h_results[k]
-            self._h_loss.copy_(row[:2 * N * 4].view(torch.float32).view(2, N))
-            self._h_return.copy_(row[self._off_ret:].view(torch.float64))
-            out.append(self._record_stats(windows=(k == n - 1)))   # window means once per call, like ia2c.py's print cadence
-        return out
+        # one vectorised pass over the pinned result slots: per-episode Python work (and the 50*E window means, which
+        # ia2c.py only prints every 10 episodes) would leave the GPU idle between calls -> window_stats() is on demand
+        res = self._h_results[:n].numpy()
+        losses = res[:, :2 * N * 4].copy().view(np.float32).reshape(n, 2, N)
+        rets = res[:, self._off_ret:self._off_ret + E * 8].copy().view(np.float64).reshape(n, E)
+        self._h_loss.copy_(torch.from_numpy(losses[-1]))
+        self._h_return.copy_(torch.from_numpy(rets[-1]))
+        self.critic_losses = (self.critic_losses + list(losses[-20:, 0]))[-20:]
+        self.actor_losses = (self.actor_losses + list(losses[-20:, 1]))[-20:]
+        self.reward_lst = (self.reward_lst + list(rets[-50:]))[-50:]
+        return [dict(critic_loss=losses[k, 0], actor_loss=losses[k, 1], ep_return=rets[k]) for k in range(n)]
 
     def _pipeline_multirank(self, host_tapes):
         """Same pipeline with torch streams/events around the per-phase entry points (the gradient exchanges sit

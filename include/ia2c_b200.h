@@ -269,12 +269,14 @@ int ia2c_train_episode_timed(const ia2c_episode_desc* d, float* host_ms_out, voi
  *   host_results   (pinned) = n_episodes x [loss float[2,N] | pad to 8 B | ep_return double[E]], ia2c_host_result_bytes.
  * On the device the two tapes share one staging region (desc.inj_u_belief must follow desc.inj_u_action at the padded
  * offset; stage_b is a second region of the same size) and desc.ep_return follows desc.loss_out the same way.  The H2D
- * copy of episode k+1 overlaps the compute of episode k on an internal copy stream; one host sync at the end.
+ * copy of episode k+1 overlaps the compute of episode k on an internal copy stream; with result_b (a second device result
+ * region of ia2c_host_result_bytes, may be NULL) the D2H of episode k also runs on its own stream under episode k+1, and the
+ * last episode's results are left in desc.loss_out / desc.ep_return; one host sync at the end.
  * Episode numbers are desc.episode .. desc.episode + n_episodes - 1. */
 size_t ia2c_host_tape_bytes(const ia2c_episode_desc* d);
 size_t ia2c_host_result_bytes(const ia2c_episode_desc* d);
-int ia2c_train_episodes_host(const ia2c_episode_desc* d, void* stage_b, int32_t n_episodes, const void* const* host_tapes,
-                             void* host_results, void* stream);
+int ia2c_train_episodes_host(const ia2c_episode_desc* d, void* stage_b, void* result_b, int32_t n_episodes,
+                             const void* const* host_tapes, void* host_results, void* stream);
 
 #ifdef __cplusplus
 }

@@ -202,9 +202,10 @@ def test_fused_rollout_rejects_unsupported_shapes():
         tr.train_episode()
 
 
-def test_pipelined_host_episodes_match_sequential_calls():
+@pytest.mark.parametrize("n", [1, 5, 6])
+def test_pipelined_host_episodes_match_sequential_calls(n):
     import torch
-    E, N, M, T, n = 40, 2, 5, 30, 5
+    E, N, M, T = 40, 2, 5, 30
     init = _random_init(N, M, seed=9)
     rng = np.random.RandomState(1)
     ua = [torch.from_numpy(rng.rand(T + 1, E, N).astype(np.float32)).pin_memory() for _ in range(n)]
@@ -217,6 +218,10 @@ def test_pipelined_host_episodes_match_sequential_calls():
         assert np.array_equal(p["ep_return"], q["ep_return"]) and np.array_equal(p["critic_loss"], q["critic_loss"])
         assert np.array_equal(p["actor_loss"], q["actor_loss"])
     assert np.array_equal(host(a.actor_params), host(b.actor_params)) and a.episode == b.episode == n
+    # the descriptor's own result region holds the LAST episode whichever of the two device regions it ran in
+    assert np.array_equal(host(a.ep_return), piped[-1]["ep_return"]) and np.array_equal(host(a.loss_out)[0], piped[-1]["critic_loss"])
+    wa, wb = a.window_stats(), b.window_stats()
+    assert np.array_equal(wa["critic_loss_window"], wb["critic_loss_window"]) and wa["mean_return"] == wb["mean_return"]
 
 
 @pytest.mark.parametrize("fused", [False, True])
