@@ -89,6 +89,7 @@ SIGNATURES = {
     "ia2c_host_tape_bytes": (C.c_size_t, [_DP]),
     "ia2c_host_result_bytes": (C.c_size_t, [_DP]),
     "ia2c_train_episodes_host": (C.c_int, [_DP, vp, vp, i32, C.POINTER(vp), vp, vp]),
+    "ia2c_train_episodes_host_p2p": (C.c_int, [_DP, C.POINTER(PeerDesc), u32, vp, vp, i32, C.POINTER(vp), vp, vp]),
 }
 
 _lib = None

@@ -701,10 +701,15 @@ extern "C" size_t ia2c_host_result_bytes(const ia2c_episode_desc* d) {
     return align8(2 * (size_t)d->N * sizeof(float)) + (size_t)d->E * sizeof(double);
 }
 
-extern "C" int ia2c_train_episodes_host(const ia2c_episode_desc* d, void* stage_b, void* result_b, int32_t n_episodes,
-                                        const void* const* host_tapes, void* host_results, void* stream) {
+// peers == nullptr: single rank (ia2c_train_episode per episode); otherwise the multi-GPU sequence with the fused
+// NVLink all-reduce + Adam after each gradient phase (desc.flags must carry SKIP_ADAM | GRAD_ONLY).
+static int episodes_host_impl(const ia2c_episode_desc* d, const ia2c_peer_desc* peers, uint32_t epoch0, void* stage_b,
+                              void* result_b, int32_t n_episodes, const void* const* host_tapes, void* host_results,
+                              void* stream) {
     if (int rc = validate(d, "ia2c_train_episodes_host")) return rc;
-    IA2C_REQUIRE(!(d->flags & IA2C_FLAG_SKIP_ADAM), "ia2c_train_episodes_host: single-rank entry point (SKIP_ADAM set)");
+    if (peers) IA2C_REQUIRE((d->flags & IA2C_FLAG_GRAD_ONLY) && (d->flags & IA2C_FLAG_SKIP_ADAM),
+                            "ia2c_train_episodes_host_p2p: desc.flags must carry SKIP_ADAM | GRAD_ONLY");
+    else IA2C_REQUIRE(!(d->flags & IA2C_FLAG_SKIP_ADAM), "ia2c_train_episodes_host: single-rank entry point (SKIP_ADAM set)");
     IA2C_REQUIRE(n_episodes > 0 && host_tapes && host_results, "ia2c_train_episodes_host: null host pointer or n_episodes=%d", n_episodes);
     const size_t n_act = (size_t)(d->T + 1) * d->E * d->N;
     const size_t off_b = align8(n_act * sizeof(float)), tape_bytes = ia2c_host_tape_bytes(d);
@@ -738,7 +743,16 @@ extern "C" int ia2c_train_episodes_host(const ia2c_episode_desc* d, void* stage_
         e.loss_out = reinterpret_cast<float*>(result[b]);
         e.ep_return = reinterpret_cast<double*>(result[b] + off_ret);
         e.episode = d->episode + (uint32_t)k;
-        if (int rc = ia2c_train_episode(&e, stream)) return rc;
+        if (!peers) {
+            if (int rc = ia2c_train_episode(&e, stream)) return rc;
+        } else {
+            const int32_t adam_step = (int32_t)e.episode + 1;   // one Adam step per net per episode
+            if (int rc = ia2c_rollout(&e, stream)) return rc;
+            if (int rc = ia2c_critic_phase(&e, stream)) return rc;                                   // gradient partials only
+            if (int rc = ia2c_allreduce_adam(&e, 0, peers, epoch0 + 2 * (uint32_t)k + 1, adam_step, stream)) return rc;
+            if (int rc = ia2c_actor_phase(&e, stream)) return rc;
+            if (int rc = ia2c_allreduce_adam(&e, 1, peers, epoch0 + 2 * (uint32_t)k + 2, adam_step, stream)) return rc;
+        }
         cudaEventRecord(g_pipe.consumed[b], s);
         char* host_slot = reinterpret_cast<char*>(host_results) + (size_t)k * res_bytes;
         if (result_b) {
@@ -765,6 +779,18 @@ extern "C" int ia2c_train_episodes_host(const ia2c_episode_desc* d, void* stage_
                 std::chrono::duration<double, std::micro>(t_done - t_begin).count() / n_episodes);
     }
     return 0;
+}
+
+extern "C" int ia2c_train_episodes_host(const ia2c_episode_desc* d, void* stage_b, void* result_b, int32_t n_episodes,
+                                        const void* const* host_tapes, void* host_results, void* stream) {
+    return episodes_host_impl(d, nullptr, 0, stage_b, result_b, n_episodes, host_tapes, host_results, stream);
+}
+
+extern "C" int ia2c_train_episodes_host_p2p(const ia2c_episode_desc* d, const ia2c_peer_desc* peers, uint32_t epoch0,
+                                            void* stage_b, void* result_b, int32_t n_episodes,
+                                            const void* const* host_tapes, void* host_results, void* stream) {
+    IA2C_REQUIRE(peers != nullptr, "ia2c_train_episodes_host_p2p: null peer descriptor");
+    return episodes_host_impl(d, peers, epoch0, stage_b, result_b, n_episodes, host_tapes, host_results, stream);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -818,21 +844,8 @@ extern "C" int ia2c_allreduce_adam(const ia2c_episode_desc* d, int32_t which, co
     for (int p = 0; p < peers->world; ++p)
         IA2C_REQUIRE(peers->inbox[p] && peers->flags[p], "ia2c_allreduce_adam: null peer buffer %d", p);
     cudaStream_t s = as_stream(stream);
-    ReduceArgs R;
-    R.partials = d->partials;
-    R.n_blocks = which == 0 ? critic_partial_blocks(d) : actor_partial_blocks(d);
-    R.P = which == 0 ? kCriticP : kActorP;
-    R.grad = which == 0 ? d->critic_grad : d->actor_grad;
-    R.grad_accum = which == 0 ? nullptr : d->actor_grad_accum;
-    R.params = which == 0 ? d->critic_params : d->actor_params;
-    R.m = which == 0 ? d->critic_m : d->actor_m;
-    R.v = which == 0 ? d->critic_v : d->actor_v;
-    R.step = which == 0 ? d->critic_step : d->actor_step;
-    R.loss_out = d->loss_out + (which == 0 ? 0 : d->N);
-    R.loss_scale = 1.f / (float)((int64_t)d->T * d->E_total);
-    R.lr = which == 0 ? d->lr_critic : d->lr_actor;
+    ReduceArgs R = make_reduce_args(*d, which, which == 0 ? critic_partial_blocks(d) : actor_partial_blocks(d));
     R.apply_adam = 1;
-    R.from_partials = 1;
     PeerArgs X;
     X.rank = peers->rank;
     X.world = peers->world;

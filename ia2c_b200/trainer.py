@@ -304,7 +304,7 @@ class IA2CTrainer:
         res_bytes = self._result_region.numel()
         if getattr(self, "_h_results", None) is None or self._h_results.shape[0] < n:
             self._h_results = torch.zeros(n, res_bytes, dtype=torch.uint8).pin_memory()
-        if self.world > 1:
+        if self.world > 1 and self.comm != "p2p":
             self._pipeline_multirank(host_tapes)
         else:
             ptrs = (C.c_void_p * n)(*[t.data_ptr() for t in host_tapes])
@@ -312,11 +312,20 @@ class IA2CTrainer:
                 self._result_region_b = torch.zeros_like(self._result_region)
             self.desc.episode = self.episode
             with torch.cuda.device(self.device):
-                _lib.check(self.lib.ia2c_train_episodes_host(C.byref(self.desc), self._stage[1].data_ptr(),
-                                                             self._result_region_b.data_ptr(), n, ptrs,
-                                                             self._h_results.data_ptr(), self._stream()),
-                           "ia2c_train_episodes_host")
+                if self.world == 1:
+                    _lib.check(self.lib.ia2c_train_episodes_host(C.byref(self.desc), self._stage[1].data_ptr(),
+                                                                 self._result_region_b.data_ptr(), n, ptrs,
+                                                                 self._h_results.data_ptr(), self._stream()),
+                               "ia2c_train_episodes_host")
+                else:   # every rank runs the same C pipeline; the gradient exchanges are the fused NVLink kernels
+                    _lib.check(self.lib.ia2c_train_episodes_host_p2p(C.byref(self.desc), C.byref(self.peers), self._epoch,
+                                                                     self._stage[1].data_ptr(), self._result_region_b.data_ptr(),
+                                                                     n, ptrs, self._h_results.data_ptr(), self._stream()),
+                               "ia2c_train_episodes_host_p2p")
+                    self._epoch += 2 * n
             self.episode += n
+            if self.world > 1:
+                self.check_comm()
         # one vectorised pass over the pinned result slots: per-episode Python work (and the 50*E window means, which
         # ia2c.py only prints every 10 episodes) would leave the GPU idle between calls -> window_stats() is on demand
         res = self._h_results[:n].numpy()

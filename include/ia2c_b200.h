@@ -277,6 +277,12 @@ size_t ia2c_host_tape_bytes(const ia2c_episode_desc* d);
 size_t ia2c_host_result_bytes(const ia2c_episode_desc* d);
 int ia2c_train_episodes_host(const ia2c_episode_desc* d, void* stage_b, void* result_b, int32_t n_episodes,
                              const void* const* host_tapes, void* host_results, void* stream);
+/* The same pipeline on every rank of a multi-GPU run (one process per GPU): after each gradient phase the fused NVLink
+ * all-reduce + Adam (ia2c_allreduce_adam) with epochs epoch0+1 .. epoch0+2*n_episodes; desc.flags = SKIP_ADAM | GRAD_ONLY.
+ * Every rank must call it with the same n_episodes. */
+int ia2c_train_episodes_host_p2p(const ia2c_episode_desc* d, const ia2c_peer_desc* peers, uint32_t epoch0, void* stage_b,
+                                 void* result_b, int32_t n_episodes, const void* const* host_tapes, void* host_results,
+                                 void* stream);
 
 #ifdef __cplusplus
 }

@@ -52,6 +52,27 @@ def main():
         if not torch.equal(p, sharded.actor_params):
             ok = False
             print(f"[rank {rank}] N={N} parameters diverged across ranks")
+        # the pipelined host-tape path (one C call per rank for p2p, torch streams for nccl): same tapes, sharded by env block
+        T, K, n_ep = sharded.T, N - 1, 4
+        rng = np.random.RandomState(N)
+        ua = [rng.rand(T + 1, E_total, N).astype(np.float32) for _ in range(n_ep)]
+        ub = [rng.rand(T + 1, E_total, N, K) for _ in range(n_ep)]
+        out_s = sharded.train_episodes_host([sharded.pack_host_tape(a[:, sl], b[:, sl]) for a, b in zip(ua, ub)])
+        out_1 = single.train_episodes_host([single.pack_host_tape(a, b) for a, b in zip(ua, ub)])
+        torch.cuda.synchronize()
+        for k in range(n_ep):
+            if not np.array_equal(out_s[k]["ep_return"], out_1[k]["ep_return"][sl]):
+                ok = False
+                print(f"[rank {rank}] N={N} comm={comm} host pipeline: episode {k} returns differ")
+        for name in ("actor_params", "critic_params"):
+            a, b = h(getattr(sharded, name)).astype(np.float64), h(getattr(single, name)).astype(np.float64)
+            err = np.abs(a - b).max() / np.abs(b).max()
+            if err > 2e-6:
+                ok = False
+                print(f"[rank {rank}] N={N} comm={comm} host pipeline {name} rel err {err:.2e}")
+        if sharded.episode != single.episode:
+            ok = False
+            print(f"[rank {rank}] episode counters differ {sharded.episode} {single.episode}")
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
