@@ -254,15 +254,13 @@ __global__ void __launch_bounds__(kPipeBlock) actor_pipe_kernel(ia2c_episode_des
 
 }  // namespace
 
-// env columns per lane.  Two columns per lane (C = 2) were measured SLOWER at every size tried (36.8 vs 26.0 us at
-// 4096 envs x 2 agents): ptxas keeps the two chains sequential under the register budget of the critic-forward warp,
-// and two co-resident blocks per SM overlap better than one block with twice the work.  Kept as a template parameter.
-static int pipe_columns(int64_t, int) { return 1; }
-int64_t actor_pipe_blocks(int64_t E, int N) { const int w = 32 * pipe_columns(E, N); return (E + w - 1) / w; }
+// env columns per lane: C = 1.  Two columns per lane were measured SLOWER at every size tried (36.8 vs 26.0 us at 4096 envs x
+// 2 agents): ptxas keeps the two chains sequential under the register budget of the critic-forward warp, and two co-resident
+// blocks per SM overlap better than one block with twice the work.  The template parameter stays for the next attempt.
+int64_t actor_pipe_blocks(int64_t E, int) { return (E + 31) / 32; }
 
 int actor_pipe_launch(const ia2c_episode_desc* d, cudaStream_t s) {
     dim3 grid((unsigned)actor_pipe_blocks(d->E, d->N), (unsigned)d->N);
-    if (pipe_columns(d->E, d->N) == 2) return launch_pdl("actor_pipe_kernel", actor_pipe_kernel<2>, grid, dim3(kPipeBlock), 0, s, *d, d->partials);
     return launch_pdl("actor_pipe_kernel", actor_pipe_kernel<1>, grid, dim3(kPipeBlock), 0, s, *d, d->partials);
 }
 
