@@ -70,6 +70,9 @@ SIGNATURES = {
     "ia2c_mlp_backward_workspace": (C.c_size_t, [i64, i32, i32]),
     "ia2c_mlp_backward": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, vp]),
     "ia2c_actor_sample": (C.c_int, [vp, vp, vp, vp, vp, i64, i32, i32, u64, u64, vp]),
+    "ia2c_mlp_forward_index": (C.c_int, [vp, vp, vp, vp, i64, i32, i32, i32, vp]),
+    "ia2c_mlp_backward_index": (C.c_int, [vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, vp]),
+    "ia2c_actor_sample_index": (C.c_int, [vp, vp, vp, vp, vp, i64, i32, i32, u64, u64, vp]),
     "ia2c_critic_loss": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, i64, i32, vp]),
     "ia2c_actor_loss": (C.c_int, [vp, vp, vp, f32, vp, vp, vp, vp, vp, i64, i32, vp]),
     "ia2c_loss_workspace": (C.c_size_t, [i64]),

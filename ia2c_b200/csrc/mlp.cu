@@ -331,6 +331,91 @@ mlp_backward_w1_kernel(const float* __restrict__ x, const float* __restrict__ dz
     }
 }
 
+// ---- index input: the row's observation is one_hot(idx, F), as a2c_test.py:57,67 builds it.  Layer 1
+// is then b1 + W1[:, idx] — the dense kernels compute exactly that (every other term is fma(w, 0, acc) = acc), so these
+// kernels return the dense kernels' bits without the F-wide row: no [rows, F] tensor is ever materialised or read.
+// Only the F-independent tail of the parameters is staged in shared memory; the W1 column is gathered through L1.
+__device__ __forceinline__ void layer1_index(const float* __restrict__ params, const float* ws, int F, int64_t idx, float (&h1)[H]) {
+#pragma unroll
+    for (int j = 0; j < H; ++j) h1[j] = fmaxf(__fadd_rn(__ldg(params + (int64_t)j * F + idx), ws[j]), 0.f);
+}
+
+template <int OMAX, bool SAMPLE>
+__global__ void __launch_bounds__(kThreads)
+mlp_forward_index_kernel(const float* __restrict__ params, const int64_t* __restrict__ idx, float* __restrict__ y,
+                         float* __restrict__ h1_out, const float* __restrict__ u, int64_t* __restrict__ actions,
+                         int64_t rows, int F, int O, int softmax, uint64_t seed, uint64_t counter) {
+    extern __shared__ float ws[];                 // parameters after W1: b1 | W2 | b2 | W3 | b3
+    const MlpLayout L0(0, O);                     // the same layout with the W1 block removed
+    for (int i = threadIdx.x; i < L0.P; i += blockDim.x) ws[i] = params[(int64_t)H * F + i];
+    __syncthreads();
+    Acts<OMAX> a;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x) {
+        layer1_index(params, ws, F, idx[r], a.h1);
+        if (h1_out) {
+#pragma unroll
+            for (int j = 0; j < H; ++j) h1_out[r * H + j] = a.h1[j];
+        }
+        tail_forward<OMAX>(ws, L0, O, SAMPLE || softmax != 0, a);
+        if (y) {
+#pragma unroll
+            for (int o = 0; o < OMAX; ++o) if (o < O) y[r * O + o] = a.y[o];
+        }
+        if (SAMPLE) {   // same sampler as actor_sample_kernel
+            const float uu = u ? u[r] : philox_uniform_f32(seed, kStreamAction, (uint32_t)(counter >> 16), (uint32_t)(counter & 0xFFFF), (uint64_t)r);
+            float s = 0.f;
+#pragma unroll
+            for (int o = 0; o < OMAX; ++o) if (o < O) s += a.y[o];
+            const float us = uu * s;
+            float c = 0.f;
+            int act = O - 1;
+            bool found = false;
+#pragma unroll
+            for (int o = 0; o < OMAX; ++o) {
+                if (o < O) {
+                    c += a.y[o];
+                    if (!found && us < c) { act = o; found = true; }
+                }
+            }
+            actions[r] = act;
+        }
+    }
+}
+
+// dW1[j][f] = sum over the rows with idx == f of dz1[r][j], rows in ascending order: the dense B2 kernel's sums exactly.
+__global__ void __launch_bounds__(kThreads)
+mlp_backward_w1_index_kernel(const int64_t* __restrict__ idx, const float* __restrict__ dz1, float* __restrict__ partials_w1,
+                             int64_t rows, int F, int rows_per_chunk) {
+    __shared__ float dz[64][H];
+    __shared__ int id_s[64];
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t r0 = (int64_t)blockIdx.y * rows_per_chunk;
+    const int64_t r1 = (r0 + rows_per_chunk < rows) ? r0 + rows_per_chunk : rows;
+    float acc[H];
+#pragma unroll
+    for (int j = 0; j < H; ++j) acc[j] = 0.f;
+    for (int64_t base = r0; base < r1; base += 64) {
+        const int n = (r1 - base) < 64 ? (int)(r1 - base) : 64;
+        __syncthreads();
+        for (int i = threadIdx.x; i < n * H; i += blockDim.x) dz[i / H][i % H] = dz1[base * H + i];
+        for (int i = threadIdx.x; i < n; i += blockDim.x) id_s[i] = (int)idx[base + i];
+        __syncthreads();
+        if (f < F) {
+#pragma unroll 8
+            for (int rr = 0; rr < n; ++rr) {
+                if (id_s[rr] == f) {
+#pragma unroll
+                    for (int j = 0; j < H; ++j) acc[j] = __fadd_rn(dz[rr][j], acc[j]);
+                }
+            }
+        }
+    }
+    if (f < F) {
+#pragma unroll
+        for (int j = 0; j < H; ++j) partials_w1[((int64_t)blockIdx.y * H + j) * F + f] = acc[j];
+    }
+}
+
 // ---- backward B3: fixed-order sum of partials into the flat gradient.
 __global__ void __launch_bounds__(kThreads)
 mlp_backward_reduce_kernel(const float* __restrict__ partials_small, int n_blocks, const float* __restrict__ partials_w1,
@@ -455,6 +540,7 @@ extern "C" int ia2c_mlp_backward(const float* params, const float* x, const floa
             if (smem > 48 * 1024) cudaFuncSetAttribute(mlp_backward_rows_kernel<OM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             mlp_backward_rows_kernel<OM, true><<<blocks_rows, kThreads, smem, s>>>(params, x, dy, h1_saved, dz1, dx, psmall, rows, F, O, softmax);
         } else {
+            if (smem > 48 * 1024) cudaFuncSetAttribute(mlp_backward_rows_kernel<OM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             mlp_backward_rows_kernel<OM, false><<<blocks_rows, kThreads, smem, s>>>(params, x, dy, h1_saved, dz1, dx, psmall, rows, F, O, softmax);
         }
         return check_launch("mlp_backward_rows_kernel");
@@ -463,6 +549,65 @@ extern "C" int ia2c_mlp_backward(const float* params, const float* x, const floa
     dim3 g2(ceil_div(F, kThreads), p.chunks);
     mlp_backward_w1_kernel<<<g2, kThreads, 0, s>>>(x, dz1, pw1, rows, F, p.rows_per_chunk);
     rc = check_launch("mlp_backward_w1_kernel");
+    if (rc) return rc;
+    mlp_backward_reduce_kernel<<<ceil_div(L.P, kThreads), kThreads, 0, s>>>(psmall, blocks_rows, pw1, p.chunks, grad, F, O, accumulate);
+    return check_launch("mlp_backward_reduce_kernel");
+}
+
+// ---- index-input entry points (one_hot(idx, F) observations; see the kernels above)
+static int launch_forward_index(const float* params, const int64_t* idx, float* y, float* h1_out, const float* u,
+                                int64_t* actions, int64_t rows, int F, int O, int softmax, uint64_t seed, uint64_t counter,
+                                bool sample, cudaStream_t s) {
+    const MlpLayout L0(0, O);
+    const int grid = (int)std::min<int64_t>(kMaxBlocks, (rows + kThreads - 1) / kThreads);
+    const size_t smem = L0.P * sizeof(float);
+    return dispatch_omax(O, [&](auto om) {
+        constexpr int OM = decltype(om)::value;
+        if (sample) mlp_forward_index_kernel<OM, true><<<grid, kThreads, smem, s>>>(params, idx, y, h1_out, u, actions, rows, F, O, 1, seed, counter);
+        else mlp_forward_index_kernel<OM, false><<<grid, kThreads, smem, s>>>(params, idx, y, h1_out, nullptr, nullptr, rows, F, O, softmax, 0, 0);
+        return check_launch("mlp_forward_index_kernel");
+    });
+}
+
+extern "C" int ia2c_mlp_forward_index(const float* params, const int64_t* idx, float* y, float* h1_out, int64_t rows,
+                                      int32_t F, int32_t O, int32_t softmax, void* stream) {
+    IA2C_REQUIRE(params && idx && y && rows > 0, "ia2c_mlp_forward_index: null pointer or rows=%lld", (long long)rows);
+    IA2C_REQUIRE(F >= 1 && O >= 1 && O <= 32, "ia2c_mlp_forward_index: F=%d O=%d unsupported", F, O);
+    return launch_forward_index(params, idx, y, h1_out, nullptr, nullptr, rows, F, O, softmax, 0, 0, false, as_stream(stream));
+}
+
+extern "C" int ia2c_actor_sample_index(const float* params, const int64_t* idx, const float* u, int64_t* actions_out,
+                                       float* probs_out, int64_t rows, int32_t F, int32_t O, uint64_t seed,
+                                       uint64_t counter, void* stream) {
+    IA2C_REQUIRE(params && idx && actions_out && rows > 0, "ia2c_actor_sample_index: null pointer or rows=%lld", (long long)rows);
+    IA2C_REQUIRE(F >= 1 && O >= 1 && O <= 32, "ia2c_actor_sample_index: F=%d O=%d unsupported", F, O);
+    return launch_forward_index(params, idx, probs_out, nullptr, u, actions_out, rows, F, O, 1, seed, counter, true, as_stream(stream));
+}
+
+extern "C" int ia2c_mlp_backward_index(const float* params, const int64_t* idx, const float* dy, const float* h1_saved,
+                                       float* grad, float* workspace, int64_t rows, int32_t F, int32_t O, int32_t softmax,
+                                       int32_t accumulate, void* stream) {
+    IA2C_REQUIRE(params && idx && dy && h1_saved && grad && workspace && rows > 0,
+                 "ia2c_mlp_backward_index: null pointer or rows=%lld (h1_saved from ia2c_mlp_forward_index is required)", (long long)rows);
+    IA2C_REQUIRE(F >= 1 && F <= 8192 && O >= 1 && O <= 32, "ia2c_mlp_backward_index: F=%d O=%d unsupported", F, O);
+    const MlpLayout L(F, O);
+    const BackwardPlan p = plan_backward(rows, F, O);   // same workspace layout as the dense backward
+    const int blocks_rows = (int)std::min<int64_t>(p.blocks_rows, (rows + kThreads - 1) / kThreads);
+    cudaStream_t s = as_stream(stream);
+    float* dz1 = workspace + p.off_dz1;
+    float* psmall = workspace + p.off_small;
+    float* pw1 = workspace + p.off_w1;
+    const size_t smem = std::max<size_t>(L.P, (size_t)(kThreads / 32) * p.n_small) * sizeof(float);
+    int rc = dispatch_omax(O, [&](auto om) {
+        constexpr int OM = decltype(om)::value;
+        if (smem > 48 * 1024) cudaFuncSetAttribute(mlp_backward_rows_kernel<OM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        mlp_backward_rows_kernel<OM, false><<<blocks_rows, kThreads, smem, s>>>(params, nullptr, dy, h1_saved, dz1, nullptr, psmall, rows, F, O, softmax);
+        return check_launch("mlp_backward_rows_kernel");
+    });
+    if (rc) return rc;
+    dim3 g2(ceil_div(F, kThreads), p.chunks);
+    mlp_backward_w1_index_kernel<<<g2, kThreads, 0, s>>>(idx, dz1, pw1, rows, F, p.rows_per_chunk);
+    rc = check_launch("mlp_backward_w1_index_kernel");
     if (rc) return rc;
     mlp_backward_reduce_kernel<<<ceil_div(L.P, kThreads), kThreads, 0, s>>>(psmall, blocks_rows, pw1, p.chunks, grad, F, O, accumulate);
     return check_launch("mlp_backward_reduce_kernel");

@@ -47,7 +47,7 @@ class _MLPFunction(torch.autograd.Function):
         rows = x2.shape[0]
         y = torch.empty(rows, action_dim, dtype=torch.float32, device=x2.device)
         # keep the layer-1 activations when a backward pass may follow: it then never re-reads x to recompute them
-        h1 = torch.empty(rows, hidden_size, dtype=torch.float32, device=x2.device) if torch.is_grad_enabled() else None
+        h1 = torch.empty(rows, hidden_size, dtype=torch.float32, device=x2.device) if any(ctx.needs_input_grad) else None
         _lib.check(lib.ia2c_mlp_forward(_lib.ptr(flat.detach()), _lib.ptr(x2), _lib.ptr(y), _lib.ptr(h1), rows, state_dim,
                                         action_dim, 1, int(softmax), _lib.stream_ptr()), "ia2c_mlp_forward")
         ctx.save_for_backward(x2, flat, h1)
@@ -69,6 +69,53 @@ class _MLPFunction(torch.autograd.Function):
                                          _lib.ptr(dx), _lib.ptr(ws), rows, state_dim, action_dim, int(softmax), 0,
                                          _lib.stream_ptr()), "ia2c_mlp_backward")
         return (dx.reshape(xshape) if dx is not None else None), grad, None, None, None
+
+
+def _is_index_input(s):
+    """Integer-typed observations are class indices standing for one_hot(idx, state_dim) rows (the
+    a2c_test.py shape, where the reference materialises F.one_hot(states, 500).float()); floats are dense features."""
+    if isinstance(s, torch.Tensor):
+        return not (s.dtype.is_floating_point or s.dtype.is_complex or s.dtype == torch.bool)
+    return np.asarray(s).dtype.kind in "iu"
+
+
+def _checked_indices(idx, state_dim, dev):
+    i = torch.as_tensor(idx).to(dev, torch.int64)
+    flat = i.reshape(-1).contiguous()
+    if flat.numel() and (int(flat.min()) < 0 or int(flat.max()) >= state_dim):   # F.one_hot raises here too
+        raise RuntimeError(f"Class values must be in [0, {state_dim}) for an index-typed observation")
+    return i, flat
+
+
+class _MLPIndexFunction(torch.autograd.Function):
+    """y = NeuralNet(one_hot(idx)) without the one-hot tensor: ia2c_mlp_forward_index / ia2c_mlp_backward_index
+    (bit-identical to _MLPFunction on the materialised rows)."""
+
+    @staticmethod
+    def forward(ctx, idx_flat, flat, state_dim, action_dim, softmax):
+        lib = _lib.load()
+        rows = idx_flat.shape[0]
+        y = torch.empty(rows, action_dim, dtype=torch.float32, device=flat.device)
+        h1 = torch.empty(rows, hidden_size, dtype=torch.float32, device=flat.device) if any(ctx.needs_input_grad) else None
+        _lib.check(lib.ia2c_mlp_forward_index(_lib.ptr(flat.detach()), _lib.ptr(idx_flat), _lib.ptr(y), _lib.ptr(h1), rows,
+                                              state_dim, action_dim, int(softmax), _lib.stream_ptr()), "ia2c_mlp_forward_index")
+        ctx.save_for_backward(idx_flat, flat, h1)
+        ctx.dims = (state_dim, action_dim, softmax)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        lib = _lib.load()
+        idx_flat, flat, h1 = ctx.saved_tensors
+        state_dim, action_dim, softmax = ctx.dims
+        rows = idx_flat.shape[0]
+        dy = gy.reshape(rows, action_dim).to(torch.float32).contiguous()
+        grad = torch.empty_like(flat)
+        ws = torch.empty(lib.ia2c_mlp_backward_workspace(rows, state_dim, action_dim), dtype=torch.float32, device=flat.device)
+        _lib.check(lib.ia2c_mlp_backward_index(_lib.ptr(flat.detach()), _lib.ptr(idx_flat), _lib.ptr(dy), _lib.ptr(h1),
+                                               _lib.ptr(grad), _lib.ptr(ws), rows, state_dim, action_dim, int(softmax), 0,
+                                               _lib.stream_ptr()), "ia2c_mlp_backward_index")
+        return None, grad, None, None, None
 
 
 class _CriticLossFunction(torch.autograd.Function):
@@ -172,7 +219,13 @@ class NeuralNet(nn.Module):
         self.l3 = _LinearView(self.flat, o3, action_dim, hidden_size)
 
     def forward(self, s):
+        """Float input: dense features [..., state_dim] (the reference's call).  Integer input: class indices [...]
+        standing for one_hot(idx, state_dim) rows — same output bits, no [rows, state_dim] tensor (index fast path)."""
         dev = self.flat.device
+        if _is_index_input(s):
+            idx, flat_idx = _checked_indices(s, self.state_dim, dev)
+            y = _MLPIndexFunction.apply(flat_idx, self.flat, self.state_dim, self.action_dim, self.b_actor)
+            return y.reshape(*idx.shape, self.action_dim)
         x = s if (isinstance(s, torch.Tensor) and s.device == dev) else torch.as_tensor(s).to(dev)
         y = _MLPFunction.apply(x.float(), self.flat, self.state_dim, self.action_dim, self.b_actor)
         return y
@@ -300,15 +353,19 @@ class ActorNetwork:
         lib = _lib.load()
         dev = self.net.flat.device
         in_dev = obs.device if isinstance(obs, torch.Tensor) else torch.device("cpu")
-        x = torch.as_tensor(obs).to(dev, torch.float32)
-        lead = x.shape[:-1]
-        x2 = x.reshape(-1, self.net.state_dim).contiguous()
+        if _is_index_input(obs):   # class indices standing for one-hot rows (index fast path)
+            idx, x2 = _checked_indices(obs, self.net.state_dim, dev)
+            lead, entry = idx.shape, lib.ia2c_actor_sample_index
+        else:
+            x = torch.as_tensor(obs).to(dev, torch.float32)
+            lead, entry = x.shape[:-1], lib.ia2c_actor_sample
+            x2 = x.reshape(-1, self.net.state_dim).contiguous()
         rows = x2.shape[0]
         actions = torch.empty(rows, dtype=torch.int64, device=dev)
         probs = torch.empty(rows, self.num_outs, dtype=torch.float32, device=dev)
-        _lib.check(lib.ia2c_actor_sample(_lib.ptr(self.net.flat.detach()), _lib.ptr(x2), None, _lib.ptr(actions),
-                                         _lib.ptr(probs), rows, self.net.state_dim, self.num_outs, self._seed,
-                                         self._calls, _lib.stream_ptr()), "ia2c_actor_sample")
+        _lib.check(entry(_lib.ptr(self.net.flat.detach()), _lib.ptr(x2), None, _lib.ptr(actions),
+                         _lib.ptr(probs), rows, self.net.state_dim, self.num_outs, self._seed,
+                         self._calls, _lib.stream_ptr()), "ia2c_actor_sample")
         self._calls += 1
         self.last_probs = probs
         if self._replay is not None:

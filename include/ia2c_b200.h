@@ -125,6 +125,18 @@ int ia2c_mlp_backward(const float* params, const float* x, const float* dy, cons
                       float* workspace, int64_t rows, int32_t F, int32_t O, int32_t softmax,
                       int32_t accumulate, void* stream);
 
+/* Index-input forms (a2c_test.py:57,67 feeds one_hot(state, F)): idx int64[rows] in [0, F) stands for the row
+ * one_hot(idx, F).  Same results, bit for bit, as the dense entry points on the materialised one-hot rows, without reading or
+ * building a [rows, F] tensor.  ia2c_mlp_backward_index needs the h1 written by ia2c_mlp_forward_index; workspace as for
+ * ia2c_mlp_backward (ia2c_mlp_backward_workspace).  Indices have no gradient. */
+int ia2c_mlp_forward_index(const float* params, const int64_t* idx, float* y, float* h1_out, int64_t rows, int32_t F,
+                           int32_t O, int32_t softmax, void* stream);
+int ia2c_mlp_backward_index(const float* params, const int64_t* idx, const float* dy, const float* h1_saved, float* grad,
+                            float* workspace, int64_t rows, int32_t F, int32_t O, int32_t softmax, int32_t accumulate,
+                            void* stream);
+int ia2c_actor_sample_index(const float* params, const int64_t* idx, const float* u, int64_t* actions_out, float* probs_out,
+                            int64_t rows, int32_t F, int32_t O, uint64_t seed, uint64_t counter, void* stream);
+
 /* ActorNetwork.sample_action (ac_nets.py:94-102): forward + Categorical(probs).sample().
  *   u float[rows] uniforms in [0,1) (injected) or NULL -> Philox(seed, counter); the sampler is
  *   inverse-CDF over q = p/sum(p) (statistically, not stream-, equivalent to torch.multinomial).

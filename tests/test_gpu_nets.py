@@ -159,3 +159,90 @@ def test_adam_matches_oracle_over_many_steps():
             pr[n] = refs[n].step(pr[n], accr[n])
     assert int(step[0]) == 25
     assert rel_err(host(p), np.stack(pr)) < 1e-6 and rel_err(host(acc), accr) < 1e-6
+
+
+def test_index_input_path_vs_reference_tape_and_dense_path(golden):
+    """integer observations stand for one_hot(idx, F) rows (a2c_test.py:57,67).  The 'taxi' tape was
+    recorded from the real ac_nets classes on materialised one-hot rows; the index path must reproduce it (1e-5) and
+    must equal the dense path on the same rows BIT FOR BIT — outputs, gradients, parameters, sampled actions."""
+    import torch
+    import torch.nn.functional as F
+    from ia2c_b200.nets import ActorNetwork, CriticNetwork
+
+    g = golden("acnets_updates.npz")
+    tag = "taxi"
+    T, E, Fd, J, A, _ = [int(x) for x in g[f"{tag}/dims"]]
+    lr_c, lr_a, beta, gamma = g[f"{tag}/hyper"]
+    torch.manual_seed(0)
+    nets = {}
+    for mode in ("index", "dense"):
+        c, a = CriticNetwork("c", Fd, J, lr_c), ActorNetwork("a", Fd, A, lr_a, beta)
+        c.net.load_flat(g[f"{tag}/critic_init"]), a.net.load_flat(g[f"{tag}/actor_init"])
+        a._seed, a._calls = 1234, 0
+        nets[mode] = (c, a)
+    for it in range(3):
+        k = lambda n: torch.from_numpy(g[f"{tag}/{it}/{n}"])
+        obs, nobs = k("obs"), k("nobs")
+        assert ((obs == 0) | (obs == 1)).all() and (obs.sum(-1) == 1).all()          # the tape's rows are one-hot
+        views = {"index": (obs.argmax(-1), nobs.argmax(-1)), "dense": (obs, nobs)}
+        out = {}
+        for mode, (o, no) in views.items():
+            critic, actor = nets[mode]
+            Q, Pr = critic.run_main(o), actor.action_distribution(o)
+            assert tuple(Q.shape) == (T, E, J) and tuple(Pr.shape) == (T, E, A)
+            acts = actor.sample_action(o)
+            with_grad = bool(g[f"{tag}/{it}/target_has_grad"])
+            qn = (critic.run_main(no, grad=with_grad) * F.one_hot(k("cnext"), J).float()).sum(-1, keepdims=True)
+            target = k("rew").unsqueeze(-1) + gamma * k("mask").unsqueeze(-1) * qn
+            critic.batch_update(o, k("cact"), target)
+            actor.batch_update(o, k("aact"), k("adv"))
+            out[mode] = dict(Q=Q.numpy(), P=Pr.numpy(), acts=acts.numpy(), probs=host(actor.last_probs),
+                             cgrad=host(critic.net.flat.grad), cpar=host(critic.net.flat), agrad=host(actor.net.flat.grad),
+                             apar=host(actor.net.flat), closs=critic.losses[-1], aloss=actor.losses[-1])
+        for name in out["index"]:
+            assert np.array_equal(out["index"][name], out["dense"][name]), (name, it)
+        o = out["index"]
+        assert rel_err(o["Q"], k("Q").numpy()) < RTOL and rel_err(o["P"], k("P").numpy()) < RTOL
+        assert rel_err(o["closs"], k("critic_loss").numpy()) < RTOL and rel_err(o["aloss"], k("actor_loss").numpy()) < RTOL
+        assert rel_err(o["cgrad"], k("critic_grad").numpy()) < RTOL and rel_err(o["cpar"], k("critic_params").numpy()) < RTOL
+        assert rel_err(o["agrad"], k("actor_grad_accum").numpy()) < RTOL and rel_err(o["apar"], k("actor_params").numpy()) < RTOL
+
+
+@pytest.mark.parametrize("rows,F,O,softmax", [(1, 500, 6, 0), (4097, 500, 6, 1), (65536, 500, 6, 0), (300, 6, 9, 0), (1000, 3000, 4, 1)])
+def test_index_kernels_equal_dense_kernels(rows, F, O, softmax):
+    import torch
+    from ia2c_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.RandomState(rows + F)
+    P = 6 * F + 6 + 36 + 6 + 6 * O + O
+    params = torch.from_numpy((rng.randn(P) * 0.3).astype(np.float32)).cuda()
+    idx = torch.from_numpy(rng.randint(0, F, size=rows)).cuda()
+    if rows > 2:
+        idx[0], idx[1] = 0, F - 1
+    x = torch.nn.functional.one_hot(idx, F).float().contiguous()
+    dy = torch.from_numpy(rng.randn(rows, O).astype(np.float32)).cuda()
+    st = _lib.stream_ptr()
+    res = {}
+    for mode in ("dense", "index"):
+        y, h1 = torch.empty(rows, O, device="cuda"), torch.empty(rows, 6, device="cuda")
+        grad = torch.empty(P, device="cuda")
+        ws = torch.empty(lib.ia2c_mlp_backward_workspace(rows, F, O), device="cuda")
+        if mode == "dense":
+            _lib.check(lib.ia2c_mlp_forward(_lib.ptr(params), _lib.ptr(x), _lib.ptr(y), _lib.ptr(h1), rows, F, O, 1, softmax, st))
+            _lib.check(lib.ia2c_mlp_backward(_lib.ptr(params), _lib.ptr(x), _lib.ptr(dy), _lib.ptr(h1), _lib.ptr(grad), None,
+                                             _lib.ptr(ws), rows, F, O, softmax, 0, st))
+        else:
+            _lib.check(lib.ia2c_mlp_forward_index(_lib.ptr(params), _lib.ptr(idx), _lib.ptr(y), _lib.ptr(h1), rows, F, O, softmax, st))
+            _lib.check(lib.ia2c_mlp_backward_index(_lib.ptr(params), _lib.ptr(idx), _lib.ptr(dy), _lib.ptr(h1), _lib.ptr(grad),
+                                                   _lib.ptr(ws), rows, F, O, softmax, 0, st))
+        res[mode] = (host(y), host(h1), host(grad))
+    for a, b, name in zip(res["dense"], res["index"], ("y", "h1", "grad")):
+        assert np.array_equal(a, b), name
+
+
+def test_index_input_rejects_out_of_range_classes():
+    import torch
+    from ia2c_b200.nets import CriticNetwork
+    c = CriticNetwork("c", 500, 6, 1e-3)
+    with pytest.raises(RuntimeError, match="Class values"):
+        c.run_main(torch.tensor([[3, 500]]))

@@ -59,9 +59,13 @@ def time_acnets(steps):
     T, E, F, O = 64, 1024, 500, 6
     rng = np.random.RandomState(0)
     out = []
-    for tag, Fd, Od in (("taxi 500->6->6->6", 500, 6), ("org 6->6->6->9", 6, 9)):
+    for tag, Fd, Od in (("taxi 500->6->6->6", 500, 6), ("taxi 500->6->6->6, index input (no one-hot tensor)", 500, 6),
+                        ("org 6->6->6->9", 6, 9)):
         idx = torch.from_numpy(rng.randint(0, Fd, size=(T, E)))
-        obs = (torch.nn.functional.one_hot(idx, Fd).float() if Fd == 500 else torch.randn(T, E, Fd)).cuda()
+        if "index" in tag:
+            obs = idx.cuda()
+        else:
+            obs = (torch.nn.functional.one_hot(idx, Fd).float() if Fd == 500 else torch.randn(T, E, Fd)).cuda()
         act = torch.from_numpy(rng.randint(0, Od, size=(T, E, 1)).astype(np.float32)).cuda()
         target = torch.randn(T, E, 1).cuda()
         adv = torch.randn(T, E, 1).cuda()
