@@ -82,7 +82,8 @@ def _is_index_input(s):
 def _checked_indices(idx, state_dim, dev):
     i = torch.as_tensor(idx).to(dev, torch.int64)
     flat = i.reshape(-1).contiguous()
-    if flat.numel() and (int(flat.min()) < 0 or int(flat.max()) >= state_dim):   # F.one_hot raises here too
+    lo, hi = torch.stack(torch.aminmax(flat)).tolist() if flat.numel() else (0, 0)   # one reduction, one sync
+    if lo < 0 or hi >= state_dim:   # F.one_hot raises here too
         raise RuntimeError(f"Class values must be in [0, {state_dim}) for an index-typed observation")
     return i, flat
 

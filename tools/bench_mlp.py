@@ -39,3 +39,9 @@ print(f"forward            {t*1e3:8.1f} us   {xb/t*1e3:7.1f} GB/s of X")
 t = timeit(lambda: _lib.check(lib.ia2c_mlp_backward(_lib.ptr(params), _lib.ptr(x), _lib.ptr(dy), _lib.ptr(h1), _lib.ptr(grad), None, _lib.ptr(ws),
                                                     rows, F, O, 1, 0, st)))
 print(f"backward (B1+B2+B3) {t*1e3:8.1f} us   {xb/t*1e3:7.1f} GB/s of X (read once: h1 saved by the forward)")
+idx = x.argmax(-1).contiguous()
+t = timeit(lambda: _lib.check(lib.ia2c_mlp_forward_index(_lib.ptr(params), _lib.ptr(idx), _lib.ptr(y), _lib.ptr(h1), rows, F, O, 1, st)))
+print(f"forward, index input   {t*1e3:8.1f} us   (8 B of idx + 24 B of h1 + {4*O} B of y per row)")
+t = timeit(lambda: _lib.check(lib.ia2c_mlp_backward_index(_lib.ptr(params), _lib.ptr(idx), _lib.ptr(dy), _lib.ptr(h1), _lib.ptr(grad), _lib.ptr(ws),
+                                                          rows, F, O, 1, 0, st)))
+print(f"backward, index input  {t*1e3:8.1f} us")
