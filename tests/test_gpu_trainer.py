@@ -195,6 +195,24 @@ def test_pipelined_actor_gradient_matches_column_kernel(E, N, M, T):
         assert np.array_equal(host(a.actor_step), host(b.actor_step))
 
 
+@pytest.mark.parametrize("T", [1, 2, 3, 4, 5, 7, 8, 9, 16, 17, 33, 64])
+@pytest.mark.parametrize("E,N", [(40, 2), (19, 3)])
+def test_pipelined_kernels_for_every_episode_length(E, N, T):
+    """The warp-specialised kernels hand data over through rings of depth 2/4/8 indexed by the time step: every
+    episode length (shorter than the pipeline, equal to a ring depth, one more, long) must give the per-step path's bytes
+    in the rollout and its gradients up to the summation order in the update (fused critic stage, pipelined actor kernel)."""
+    M = 5
+    init = _random_init(N, M, seed=T)
+    a = make_trainer(E, N, M, init, seed=6, steps_per_episode=T, max_episode_steps=min(T, 30), fused_rollout=False, actor_kernel="columns")
+    b = make_trainer(E, N, M, init, seed=6, steps_per_episode=T, max_episode_steps=min(T, 30), fused_rollout=True, actor_kernel="pipe")
+    la, lb = a.train_episode(sync_stats=True), b.train_episode(sync_stats=True)
+    for name in ROLLOUT_OUTPUTS:
+        assert np.array_equal(host(getattr(a, name)), host(getattr(b, name))), name
+    for name in UPDATE_OUTPUTS:
+        assert rel_err(host(getattr(b, name)), host(getattr(a, name))) < 2e-6, name
+    assert rel_err(lb["critic_loss"], la["critic_loss"]) < 2e-6 and rel_err(lb["actor_loss"], la["actor_loss"]) < 2e-6
+
+
 def test_fused_rollout_rejects_unsupported_shapes():
     from ia2c_b200 import _lib
     tr = make_trainer(4, 9, 5, _random_init(9, 5, seed=1), fused_rollout=True)
