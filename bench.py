@@ -348,6 +348,18 @@ def run_ours(args):
     barrier()
     e2e_wall_ms = (time.perf_counter() - t0) * 1e3
     e2e_ms = max_over_ranks(max(s.elapsed_time(e), e2e_wall_ms))
+    # the e2e pipeline runs at the rate of its one pinned H2D copy per step: report that rate on this box next to it
+    probe_dst = torch.empty_like(tapes[0], device=dev)
+    for _ in range(3):
+        probe_dst.copy_(tapes[0], non_blocking=True)
+    s, e = ev(), ev()
+    s.record()
+    for j in range(20):
+        probe_dst.copy_(tapes[j % n_bufs], non_blocking=True)
+    e.record()
+    e.synchronize()
+    h2d_us = s.elapsed_time(e) / 20 * 1e3
+    del probe_dst
     # keep the same load running until the clock sampler (rank 0) has data; the decision is COLLECTIVE so that every rank
     # runs the same number of extra episodes (the gradient exchange needs all ranks in every episode)
     for _ in range(50):
@@ -388,10 +400,12 @@ def run_ours(args):
         "back_to_back_ms_per_step": b2b_ms / K,
         "e2e": {"value": units * K / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms / K, "wall_ms_per_step": e2e_wall_ms / K,
+                "h2d_copy_us_alone": h2d_us, "h2d_gbs_alone": h2d / (h2d_us * 1e-6) / 1e9,
                 "api": ("IA2CTrainer.train_episodes_host -> ia2c_train_episodes_host (C ABI, pinned host tapes in, losses + returns "
                         "out per episode; one H2D and one D2H copy per episode, H2D of episode k+1 overlaps episode k; one sync per "
                         "50 episodes)") if world == 1 else
-                       "IA2CTrainer.train_episodes_host (torch copy stream + per-phase C-ABI calls + NCCL all-reduce)"},
+                       "IA2CTrainer.train_episodes_host -> ia2c_train_episodes_host_p2p (the same pipeline on every rank, fused NVLink "
+                       "all-reduce + Adam after each gradient phase; the ranks share the host's PCIe bandwidth)"},
         "gpu_launches": int(launches),
         "roofline": {"kernel": kname, "bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
                      "traffic": NCU_ROLLOUT_DRAM_BYTES if (fused and N == 2 and E_gpu == 4096) else None, "bytes_per_launch": traj_bytes, "us_per_launch": rollout_us,
