@@ -45,22 +45,31 @@ __host__ __device__ inline ReduceArgs make_reduce_args(const ia2c_episode_desc& 
     return R;
 }
 
-__device__ __forceinline__ void adam_update(float& p, float& m, float& v, float g, int t, double lr) {
+// Adam's bias corrections for step t: {lr / (1 - b1^t) as float, sqrt(1 - b2^t) as float}.  Two fp64 pow() calls: computed by
+// ONE thread per block while the others' partial-row loads are in flight, and handed over through shared memory.
+struct AdamBias { float step_size, bc2_sqrt; };
+__device__ __forceinline__ AdamBias adam_bias(int t, double lr) {
     const double b1 = 0.9, b2 = 0.999;
     const double bc1 = 1.0 - pow(b1, (double)t), bc2 = 1.0 - pow(b2, (double)t);
-    const float step_size = (float)(lr / bc1), bc2_sqrt = (float)sqrt(bc2);
+    AdamBias a;
+    a.step_size = (float)(lr / bc1);
+    a.bc2_sqrt = (float)sqrt(bc2);
+    return a;
+}
+__device__ __forceinline__ void adam_update(float& p, float& m, float& v, float g, const AdamBias& a) {
+    const double b1 = 0.9, b2 = 0.999;
     const float mi = m + (g - m) * (float)(1.0 - b1);
     const float vi = v * (float)b2 + (float)(1.0 - b2) * g * g;
     m = mi;
     v = vi;
-    p = p - step_size * (mi / (sqrtf(vi) / bc2_sqrt + 1e-8f));
+    p = p - a.step_size * (mi / (sqrtf(vi) / a.bc2_sqrt + 1e-8f));
 }
 
 constexpr int kReduceSlices = 32;
 
 
 // what happens to entry i of agent n once its sum s is known (shared by both reduction routes)
-__device__ __forceinline__ void finish_entry(const ReduceArgs& R, int n, int i, float s) {
+__device__ __forceinline__ void finish_entry(const ReduceArgs& R, int n, int i, float s, const AdamBias& bias) {
     const int P = R.P;
     if (R.from_partials) {
         if (i == P) s *= R.loss_scale;
@@ -69,14 +78,13 @@ __device__ __forceinline__ void finish_entry(const ReduceArgs& R, int n, int i, 
     if (i == P) {
         R.loss_out[n] = s;
     } else if (R.apply_adam) {
-        const int t = __ldcg(R.step + n);    // already incremented by the gradient kernel / apply entry
         const int64_t k = (int64_t)n * P + i;
         float g = s;
         if (R.grad_accum) {                  // the reference's actor never zeroes its gradients (Q2)
             g += R.grad_accum[k];
             R.grad_accum[k] = g;
         }
-        adam_update(R.params[k], R.m[k], R.v[k], g, t, R.lr);
+        adam_update(R.params[k], R.m[k], R.v[k], g, bias);
     }
 }
 

@@ -349,6 +349,9 @@ __global__ void __launch_bounds__(32 * kReduceSlices) reduce_adam_kernel(ReduceA
     const int col = threadIdx.x & 31, slice = threadIdx.x >> 5;
     const int i = blockIdx.y * 32 + col;
     __shared__ float part[kReduceSlices][33];
+    __shared__ AdamBias bias;
+    if (threadIdx.x == blockDim.x - 1 && R.apply_adam)   // step[n] was already incremented by the gradient kernel / apply entry
+        bias = adam_bias(__ldcg(R.step + n), R.lr);
     float s = 0.f;
     if (i <= P) {
         if (R.from_partials) {
@@ -372,7 +375,7 @@ __global__ void __launch_bounds__(32 * kReduceSlices) reduce_adam_kernel(ReduceA
     if (slice != 0 || i > P) return;
 #pragma unroll
     for (int k = 1; k < kReduceSlices; ++k) s += part[k][col];
-    finish_entry(R, n, i, s);
+    finish_entry(R, n, i, s, bias);
 }
 
 __global__ void bump_steps_kernel(int32_t* step, int n) {
@@ -517,7 +520,10 @@ __global__ void __launch_bounds__(32 * kReduceSlices) allreduce_adam_kernel(Redu
                                                                             int chunks_per_agent) {
     __shared__ float part[kReduceSlices][33];
     __shared__ int timeout;
-    pdl_prologue();
+    __shared__ AdamBias bias;
+    pdl_release();
+    if (threadIdx.x == blockDim.x - 1) bias = adam_bias(X.t, R.lr);   // from launch arguments only: overlaps the predecessor's tail
+    pdl_wait();
     const int P = R.P, col = threadIdx.x & 31, slice = threadIdx.x >> 5;
     const int parity = (int)(X.epoch & 1u);
     if (threadIdx.x == 0) timeout = 0;
@@ -576,7 +582,7 @@ __global__ void __launch_bounds__(32 * kReduceSlices) allreduce_adam_kernel(Redu
                     g += R.grad_accum[k];
                     R.grad_accum[k] = g;
                 }
-                adam_update(R.params[k], R.m[k], R.v[k], g, X.t, R.lr);
+                adam_update(R.params[k], R.m[k], R.v[k], g, bias);
             }
         }
         __syncthreads();
