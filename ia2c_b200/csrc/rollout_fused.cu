@@ -13,7 +13,8 @@
 //                                      registers) -> sample.  Carries the recurrence env -> action -> env.
 //   warp 2  B  "belief"  (step it-2)   the K fp64 belief updates (exact operation order), predicted actions,
 //                                      partner mode.  Carries the recurrence posterior(t-1) -> posterior(t).
-//   warp 3  R  "draws"   (step it)     the step's uniforms — device Philox4x32-10 or the injected tapes; then
+//   warp 3  R  "draws"   (step it)     the step's belief uniforms — device Philox4x32-10 or the injected tapes (the action
+//                                      uniforms are drawn by warp 2, which has the slack); then
 //           Cb "backprop"(obs  it-5)   ONE backward per observation with both output-gradient contributions
 //                                      it receives (W3/W2 rows in registers); owns the W3/b3/W2/b2 gradient and
 //                                      hands dz1 back to warp 0.  147 accumulators stay in registers all episode.
@@ -90,30 +91,35 @@ __global__ void __launch_bounds__(kBlock) rollout_fused_kernel(ia2c_episode_desc
     const int T = d.T;
     const int n_iter = CRITIC ? T + 7 : T + 3;   // steps 0..T through R(0) A(-1) B(-2); rows through Cf(-4), observations through Cb(-5)
 
-    // ---- R: uniforms for step t (device Philox or the injected tapes) -> shared-memory rings.  Executed by warp 0
-    //         at the top of each of its iterations (it shares the warp with the critic-forward stage).
+    // ---- R: uniforms for step t (device Philox or the injected tapes) -> shared-memory rings, in two halves so that they
+    //         can ride on different warps: with the critic stages present the backprop warp (the heaviest: 190
+    //         instructions of backward per step) only makes the belief draws and the belief warp makes the action draws.
     // Injected tapes are fetched TWO steps ahead into registers (freshly copied tapes sit in HBM: a load issued in the
     // iteration that needs it would hold the whole block at the barrier for a DRAM round trip).
-    struct Tape { float ua; double ub[K]; } tp0, tp1;
     const bool inj_a = d.inj_u_action != nullptr, inj_b = d.inj_u_belief != nullptr;
-    auto tape_fetch = [&](Tape& tp, int t) {
-        if (t <= T && agent) {
+    float tua0 = 0.f, tua1 = 0.f;
+    struct TapeB { double ub[K]; } tb0, tb1;
+    auto fetch_a = [&](float& ua, int t) {
+        if (inj_a && t <= T && agent) ua = __ldg(d.inj_u_action + ((int64_t)t * E + e) * N + i);
+    };
+    auto fetch_b = [&](TapeB& tp, int t) {
+        if (inj_b && t <= T && agent) {
             const int64_t row = ((int64_t)t * E + e) * N + i;
-            if (inj_a) tp.ua = __ldg(d.inj_u_action + row);
-            if (inj_b) {
 #pragma unroll
-                for (int jj = 0; jj < K; ++jj) tp.ub[jj] = __ldg(d.inj_u_belief + row * K + jj);
-            }
+            for (int jj = 0; jj < K; ++jj) tp.ub[jj] = __ldg(d.inj_u_belief + row * K + jj);
         }
     };
-    auto draw_init = [&]() {
-        if (inj_a || inj_b) { tape_fetch(tp0, 0); tape_fetch(tp1, 1); }
-    };
-    auto draw_from = [&](Tape& tp, int t) {
-        if (t <= T && agent) {
-            ua_s[t & 1][lane] = inj_a ? tp.ua
+    auto draw_action_init = [&]() { fetch_a(tua0, 0); fetch_a(tua1, 1); };
+    auto draw_belief_init = [&]() { fetch_b(tb0, 0); fetch_b(tb1, 1); };
+    auto draw_action_from = [&](float& ua, int t) {
+        if (t <= T && agent)
+            ua_s[t & 1][lane] = inj_a ? ua
                                       : philox_uniform_f32(d.seed, kStreamAction, d.episode, (uint32_t)t,
                                                            (uint64_t)((d.env_offset + e) * N + i));
+        fetch_a(ua, t + 2);
+    };
+    auto draw_belief_from = [&](TapeB& tp, int t) {
+        if (t <= T && agent) {
             if (inj_b) {
 #pragma unroll
                 for (int jj = 0; jj < K; ++jj) ub_s[t & 3][jj][lane] = tp.ub[jj];
@@ -127,10 +133,13 @@ __global__ void __launch_bounds__(kBlock) rollout_fused_kernel(ia2c_episode_desc
                 }
             }
         }
-        if (inj_a || inj_b) tape_fetch(tp, t + 2);
+        fetch_b(tp, t + 2);
     };
-    auto draw_step = [&](int t) {
-        if (t & 1) draw_from(tp1, t); else draw_from(tp0, t);
+    auto draw_action = [&](int t) {
+        if (t & 1) draw_action_from(tua1, t); else draw_action_from(tua0, t);
+    };
+    auto draw_belief = [&](int t) {
+        if (t & 1) draw_belief_from(tb1, t); else draw_belief_from(tb0, t);
     };
 
     if (role == 1) {
@@ -239,7 +248,9 @@ __global__ void __launch_bounds__(kBlock) rollout_fused_kernel(ia2c_episode_desc
 #pragma unroll
         for (int jj = 0; jj < K; ++jj) last_pred[jj] = 0;
         uint8_t* ppred_p = d.partner_pred + e * N + i;
+        if (CRITIC) draw_action_init();
         for (int it = 0; it < n_iter; ++it) {
+            if (CRITIC) draw_action(it);      // stage R's action half rides on this warp when the critic stages exist
             const int t = it - 2;
             if (t >= 0 && t <= T) {
                 const int64_t row = ((int64_t)t * E + e) * N + i;
@@ -315,9 +326,9 @@ __global__ void __launch_bounds__(kBlock) rollout_fused_kernel(ia2c_episode_desc
         }
     } else if (!CRITIC) {
         // ================================================================ R alone: draws (no critic stage)
-        if (role == 3) draw_init();
+        if (role == 3) { draw_action_init(); draw_belief_init(); }
         for (int it = 0; it < n_iter; ++it) {
-            if (role == 3) draw_step(it);
+            if (role == 3) { draw_action(it); draw_belief(it); }
             __syncthreads();
         }
     } else {
@@ -416,9 +427,9 @@ __global__ void __launch_bounds__(kBlock) rollout_fused_kernel(ia2c_episode_desc
     float2 gA[GA];
 #pragma unroll
     for (int k = 0; k < GA; ++k) gA[k] = make_float2(0.f, 0.f);
-    draw_init();
+    draw_belief_init();
     for (int it = 0; it < n_iter; ++it) {
-        draw_step(it);               // stage R shares this warp
+        draw_belief(it);             // stage R's belief half shares this warp
         const int t = it - 5;
         if (t >= 0 && t <= T) {
             int jt = -1, nja_prev = -1;
