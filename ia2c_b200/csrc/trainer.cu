@@ -498,23 +498,32 @@ static int run_reduce(const ia2c_episode_desc* d, int which, int from_partials, 
 // Instead of reduce kernel -> NCCL all-reduce -> Adam kernel (three launches and a ~20 us small-message
 // collective), ONE kernel per rank does all of it over peer-mapped ("symmetric") buffers:
 //   1. sum this rank's per-block partials for a chunk of 32 entries              (fixed order)
-//   2. PUSH the 32 sums into every peer's inbox slot [parity][my rank]           (plain stores over NVLink)
-//   3. system-scope fence, then raise flag[chunk][my rank] = epoch on every peer
-//   4. spin (bounded) until flag[chunk][r] == epoch for every rank r
-//   5. add the world's contributions in RANK order (every rank computes bit-identical sums) and apply Adam.
+//   2. PUSH each sum into every peer's inbox slot [parity][my rank] as ONE 8-byte word {value, epoch}: the message
+//      carries its own flag (the low-latency protocol of small-message collectives), so there is no separate
+//      flag store, no system-scope fence and no second NVLink hop on the critical path
+//   3. poll (bounded) the world's words for this entry in the own inbox until each carries this epoch
+//   4. add the contributions in RANK order (every rank computes bit-identical sums) and apply Adam.
 // Chunks are independent, so transfer and arithmetic of different chunks overlap; the grid is persistent
 // (<= one resident wave) so a block never waits for a peer block that cannot be scheduled.  Inboxes are
-// double-buffered by epoch parity: a peer can be at most one exchange ahead of this rank.
+// double-buffered by epoch parity: a peer can be at most one exchange ahead of this rank, and a slot's previous
+// content carries epoch - 2, never this epoch.  Epoch 0 is the empty inbox.
 struct PeerArgs {
     int rank, world;
-    float* inbox[8];
-    uint32_t* flags[8];
+    uint2* inbox[8];             // 8-byte words {float bits, epoch}
     int32_t* error;
     uint32_t epoch;
     int t;                       // Adam step number of this update (host-tracked in the multi-rank path)
-    int64_t inbox_base, stride;  // float offset of this phase's region; floats per (parity, rank) slot = N * (P+1)
-    int64_t flag_base;           // word offset of this phase's flags
+    int64_t inbox_base, stride;  // word offset of this phase's region; words per (parity, rank) slot = N * (P+1)
 };
+
+__device__ __forceinline__ void st_word_sys(uint2* p, float v, uint32_t epoch) {
+    asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(v)), "r"(epoch) : "memory");
+}
+__device__ __forceinline__ uint2 ld_word_sys(const uint2* p) {
+    uint2 w;
+    asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(w.x), "=r"(w.y) : "l"(p) : "memory");
+    return w;
+}
 
 __global__ void __launch_bounds__(32 * kReduceSlices) allreduce_adam_kernel(ReduceArgs R, PeerArgs X, int total_chunks,
                                                                             int chunks_per_agent) {
@@ -545,33 +554,25 @@ __global__ void __launch_bounds__(32 * kReduceSlices) allreduce_adam_kernel(Redu
         }
         part[slice][col] = s;
         __syncthreads();
-        const int64_t idx = (int64_t)n * (P + 1) + i;
         if (slice == 0 && i <= P) {
 #pragma unroll
             for (int k = 1; k < kReduceSlices; ++k) s += part[k][col];
             if (i == P) s *= R.loss_scale;
-            const int64_t slot = X.inbox_base + ((int64_t)parity * X.world + X.rank) * X.stride + idx;
-            for (int p = 0; p < X.world; ++p) X.inbox[p][slot] = s;          // NVLink stores (self included)
-            __threadfence_system();
-        }
-        __syncthreads();
-        if (threadIdx.x < X.world) {                                         // one signalling/waiting thread per peer
-            const int p = threadIdx.x;
-            const int64_t f = X.flag_base + (int64_t)c * X.world;
-            *(volatile uint32_t*)(X.flags[p] + f + X.rank) = X.epoch;        // raise my flag on peer p
-            volatile uint32_t* mine = X.flags[X.rank] + f + p;               // wait for peer p's flag on me
-            int spins = 0;
-            while (*mine != X.epoch) {
-                __nanosleep(64);
-                if (++spins > (1 << 22)) { timeout = 1; break; }             // ~ 0.3 s: report instead of hanging
-            }
-            __threadfence_system();
-        }
-        __syncthreads();
-        if (slice == 0 && i <= P) {
+            const int64_t idx = (int64_t)n * (P + 1) + i;
+            const int64_t mine = X.inbox_base + ((int64_t)parity * X.world + X.rank) * X.stride + idx;
+            for (int p = 0; p < X.world; ++p) st_word_sys(X.inbox[p] + mine, s, X.epoch);   // NVLink stores (self included)
             float g = 0.f;
-            for (int r = 0; r < X.world; ++r)                                // rank order: identical sums on every rank
-                g += __ldcv(X.inbox[X.rank] + X.inbox_base + ((int64_t)parity * X.world + r) * X.stride + idx);
+            for (int r = 0; r < X.world; ++r) {                              // rank order: identical sums on every rank
+                const uint2* w = X.inbox[X.rank] + X.inbox_base + ((int64_t)parity * X.world + r) * X.stride + idx;
+                uint2 m = ld_word_sys(w);
+                int spins = 0;
+                while (m.y != X.epoch) {
+                    __nanosleep(32);
+                    if (++spins > (1 << 22)) { timeout = 1; break; }         // ~ 0.3 s: report instead of hanging
+                    m = ld_word_sys(w);
+                }
+                g += __uint_as_float(m.x);
+            }
             R.grad[idx] = g;
             if (i == P) {
                 R.loss_out[n] = g;
@@ -591,13 +592,11 @@ __global__ void __launch_bounds__(32 * kReduceSlices) allreduce_adam_kernel(Redu
 }
 
 static void phase_regions(const ia2c_episode_desc* d, int world, int which, int64_t& inbox_base, int64_t& stride,
-                          int64_t& flag_base, int& chunks_per_agent) {
+                          int& chunks_per_agent) {
     const int64_t stride_c = (int64_t)d->N * (kCriticP + 1), stride_a = (int64_t)d->N * (kActorP + 1);
-    const int chunks_c = ceil_div(kCriticP + 1, 32), chunks_a = ceil_div(kActorP + 1, 32);
     inbox_base = which == 0 ? 0 : 2 * world * stride_c;
     stride = which == 0 ? stride_c : stride_a;
-    flag_base = which == 0 ? 0 : (int64_t)d->N * chunks_c * world;
-    chunks_per_agent = which == 0 ? chunks_c : chunks_a;
+    chunks_per_agent = ceil_div((which == 0 ? kCriticP : kActorP) + 1, 32);
 }
 
 static int check_update_ptrs(const ia2c_episode_desc* d, const char* who) {
@@ -832,7 +831,7 @@ extern "C" int ia2c_train_episode_timed(const ia2c_episode_desc* d, float* host_
 
 extern "C" size_t ia2c_peer_inbox_floats(const ia2c_episode_desc* d, int32_t world) {
     if (!d || world < 1) return 0;
-    return (size_t)2 * world * d->N * ((kCriticP + 1) + (kActorP + 1));
+    return (size_t)2 * 2 * world * d->N * ((kCriticP + 1) + (kActorP + 1));   // 8-byte words {value, epoch}, two parities
 }
 extern "C" size_t ia2c_peer_flag_words(const ia2c_episode_desc* d, int32_t world) {
     if (!d || world < 1) return 0;
@@ -848,22 +847,19 @@ extern "C" int ia2c_allreduce_adam(const ia2c_episode_desc* d, int32_t which, co
                  "ia2c_allreduce_adam: bad peer descriptor");
     IA2C_REQUIRE(epoch > 0 && adam_step > 0, "ia2c_allreduce_adam: epoch and adam_step start at 1");
     for (int p = 0; p < peers->world; ++p)
-        IA2C_REQUIRE(peers->inbox[p] && peers->flags[p], "ia2c_allreduce_adam: null peer buffer %d", p);
+        IA2C_REQUIRE(peers->inbox[p] && ((uintptr_t)peers->inbox[p] & 7) == 0, "ia2c_allreduce_adam: null or misaligned peer inbox %d", p);
     cudaStream_t s = as_stream(stream);
     ReduceArgs R = make_reduce_args(*d, which, which == 0 ? critic_partial_blocks(d) : actor_partial_blocks(d));
     R.apply_adam = 1;
     PeerArgs X;
     X.rank = peers->rank;
     X.world = peers->world;
-    for (int p = 0; p < 8; ++p) {
-        X.inbox[p] = p < peers->world ? peers->inbox[p] : nullptr;
-        X.flags[p] = p < peers->world ? peers->flags[p] : nullptr;
-    }
+    for (int p = 0; p < 8; ++p) X.inbox[p] = p < peers->world ? reinterpret_cast<uint2*>(peers->inbox[p]) : nullptr;
     X.error = peers->error;
     X.epoch = epoch;
     X.t = adam_step;
     int chunks_per_agent;
-    phase_regions(d, peers->world, which, X.inbox_base, X.stride, X.flag_base, chunks_per_agent);
+    phase_regions(d, peers->world, which, X.inbox_base, X.stride, chunks_per_agent);
     const int total = d->N * chunks_per_agent;
     const int grid = std::min(total, kSMs);          // persistent: every block is resident
     return launch_pdl("allreduce_adam_kernel", allreduce_adam_kernel, dim3(grid), dim3(32 * kReduceSlices), 0, s, R, X, total, chunks_per_agent);

@@ -246,10 +246,11 @@ int ia2c_apply_adam(const ia2c_episode_desc* d, int32_t which, void* stream);
 /* Multi-GPU: fused gradient all-reduce + Adam over NVLink peer memory, ONE kernel per optimiser phase instead of
  * reduce -> NCCL all-reduce -> Adam.  Run it after the phase's gradient kernel (ia2c_rollout with
  * IA2C_FLAG_FUSED_CRITIC, or ia2c_critic_phase / ia2c_actor_phase with IA2C_FLAG_SKIP_ADAM ... see trainer.py).
- * inbox[p] / flags[p] are rank p's symmetric buffers mapped into this process (ia2c_peer_inbox_floats floats,
- * ia2c_peer_flag_words zero-initialised 32-bit words).  epoch increases by one per call on every rank (same value
- * on all ranks); adam_step is the Adam step number of this update.  Every rank must launch it; *error is set to 1
- * if a peer does not arrive within the spin budget (the kernel then returns instead of hanging). */
+ * inbox[p] is rank p's symmetric buffer mapped into this process (ia2c_peer_inbox_floats floats, 8-byte aligned,
+ * zero-initialised): every gradient entry travels as ONE 8-byte word {value, epoch}, so a message carries its own flag
+ * (flags[] is unused and may be NULL; kept for layout compatibility).  epoch starts at 1 and increases by one per call on
+ * every rank (same value on all ranks); adam_step is the Adam step number of this update.  Every rank must launch it;
+ * *error is set to 1 if a peer does not arrive within the spin budget (the kernel then returns instead of hanging). */
 typedef struct ia2c_peer_desc {
     int32_t rank, world;       /* world <= 8 (one NVSwitch domain) */
     float* inbox[8];
