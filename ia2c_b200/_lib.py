@@ -20,6 +20,7 @@ FLAG_FUSED_CRITIC = 4
 FLAG_GRAD_ONLY = 8
 FLAG_ACTOR_COLUMNS = 16
 BELIEF_RECORD = 8
+ABI_VERSION = 2
 ACTOR_P = 105
 CRITIC_P = 147
 
@@ -50,7 +51,8 @@ class EpisodeDesc(C.Structure):
 
 class PeerDesc(C.Structure):
     """Mirror of ``ia2c_peer_desc``."""
-    _fields_ = [("rank", i32), ("world", i32), ("inbox", vp * 8), ("flags", vp * 8), ("error", vp)]
+    _fields_ = [("rank", i32), ("world", i32), ("inbox", vp * 8), ("mc_inbox", vp), ("error", vp * 8),
+                ("timeout_us", u32), ("reserved", u32)]
 
 
 _DP = C.POINTER(EpisodeDesc)
@@ -66,6 +68,7 @@ SIGNATURES = {
     "ia2c_belief_update_dense": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, vp]),
     "ia2c_belief_update_pairs": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, u64, u32, u32, i64, vp]),
     "ia2c_debug_divide": (C.c_int, [vp, vp, vp, vp, i64, vp]),
+    "ia2c_debug_fp32_peak": (C.c_int, [vp, i32, i32, i32, C.POINTER(f64), vp]),
     "ia2c_mlp_forward": (C.c_int, [vp, vp, vp, vp, i64, i32, i32, i32, i32, vp]),
     "ia2c_mlp_backward_workspace": (C.c_size_t, [i64, i32, i32]),
     "ia2c_mlp_backward": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, vp]),
@@ -83,16 +86,17 @@ SIGNATURES = {
     "ia2c_critic_phase": (C.c_int, [_DP, vp]),
     "ia2c_actor_phase": (C.c_int, [_DP, vp]),
     "ia2c_apply_adam": (C.c_int, [_DP, i32, vp]),
-    "ia2c_peer_inbox_floats": (C.c_size_t, [_DP, i32]),
-    "ia2c_peer_flag_words": (C.c_size_t, [_DP, i32]),
+    "ia2c_peer_inbox_bytes": (C.c_size_t, [_DP, i32]),
     "ia2c_allreduce_adam": (C.c_int, [_DP, i32, C.POINTER(PeerDesc), u32, i32, vp]),
     "ia2c_train_episode": (C.c_int, [_DP, vp]),
     "ia2c_train_episode_host": (C.c_int, [_DP, vp, vp, vp, vp, vp]),
     "ia2c_train_episode_timed": (C.c_int, [_DP, vp, vp]),
     "ia2c_host_tape_bytes": (C.c_size_t, [_DP]),
     "ia2c_host_result_bytes": (C.c_size_t, [_DP]),
-    "ia2c_train_episodes_host": (C.c_int, [_DP, vp, vp, i32, C.POINTER(vp), vp, vp]),
-    "ia2c_train_episodes_host_p2p": (C.c_int, [_DP, C.POINTER(PeerDesc), u32, vp, vp, i32, C.POINTER(vp), vp, vp]),
+    "ia2c_host_pipe_create": (C.c_int, [C.POINTER(vp)]),
+    "ia2c_host_pipe_destroy": (C.c_int, [vp]),
+    "ia2c_train_episodes_host": (C.c_int, [_DP, vp, vp, vp, i32, C.POINTER(vp), vp, vp]),
+    "ia2c_train_episodes_host_p2p": (C.c_int, [_DP, vp, C.POINTER(PeerDesc), u32, vp, vp, i32, C.POINTER(vp), vp, vp]),
 }
 
 _lib = None
@@ -121,7 +125,7 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
         fn.restype = res
         fn.argtypes = args
-    if lib.ia2c_abi_version() != 1:
+    if lib.ia2c_abi_version() != ABI_VERSION:
         raise ImportError("ia2c_b200: ABI version mismatch between _lib.py and libia2c_b200.so")
     _lib = lib
     return lib

@@ -498,44 +498,60 @@ static int run_reduce(const ia2c_episode_desc* d, int which, int from_partials, 
 // Instead of reduce kernel -> NCCL all-reduce -> Adam kernel (three launches and a ~20 us small-message
 // collective), ONE kernel per rank does all of it over peer-mapped ("symmetric") buffers:
 //   1. sum this rank's per-block partials for a chunk of 32 entries              (fixed order)
-//   2. PUSH each sum into every peer's inbox slot [parity][my rank] as ONE 8-byte word {value, epoch}: the message
-//      carries its own flag (the low-latency protocol of small-message collectives), so there is no separate
-//      flag store, no system-scope fence and no second NVLink hop on the critical path
-//   3. poll (bounded) the world's words for this entry in the own inbox until each carries this epoch
+//   2. PUSH each sum into every peer's inbox slot [parity][my rank] as ONE naturally aligned 64-bit word
+//      {epoch << 32 | float bits} with a single st.relaxed.sys.u64 (single-copy atomic: the word cannot tear), so the
+//      message carries its own flag — no separate flag store, no system-scope fence, no second NVLink hop.  With a
+//      multicast (NVLS) mapping one multimem.st reaches all inboxes through the switch instead of `world` stores
+//   3. poll (bounded by a wall-clock budget) the world's words for this entry in the own inbox until each carries
+//      this epoch
 //   4. add the contributions in RANK order (every rank computes bit-identical sums) and apply Adam.
 // Chunks are independent, so transfer and arithmetic of different chunks overlap; the grid is persistent
 // (<= one resident wave) so a block never waits for a peer block that cannot be scheduled.  Inboxes are
-// double-buffered by epoch parity: a peer can be at most one exchange ahead of this rank, and a slot's previous
-// content carries epoch - 2, never this epoch.  Epoch 0 is the empty inbox.
+// double-buffered by epoch parity: kernels are stream-ordered on every rank, so when a rank has finished exchange e
+// every peer has at least started e (i.e. finished e-1) — a peer can be at most one exchange ahead, and a slot's
+// previous content carries epoch - 2, never this epoch.  Epoch 0 is the empty inbox.
+// Failure: a chunk whose words do not all arrive in time applies NOTHING (no gradient, no Adam, no step counter),
+// the block stops, and the error word of EVERY rank is raised; a rank whose error word is set turns all later
+// exchanges into no-ops, so parameters are never stepped with a stale or partial sum and the run fails loudly at the
+// host's next check (trainer.py: check_comm — before statistics, checkpoints and after bench regions).
 struct PeerArgs {
     int rank, world;
-    uint2* inbox[8];             // 8-byte words {float bits, epoch}
-    int32_t* error;
+    unsigned long long* inbox[8];   // 64-bit words {epoch << 32 | float bits}
+    unsigned long long* mc_inbox;   // multicast mapping or null
+    int32_t* error[8];
     uint32_t epoch;
-    int t;                       // Adam step number of this update (host-tracked in the multi-rank path)
-    int64_t inbox_base, stride;  // word offset of this phase's region; words per (parity, rank) slot = N * (P+1)
+    int t;                          // Adam step number of this update (host-tracked in the multi-rank path)
+    int64_t stride;                 // words per (parity, rank) slot = N * (kCriticP + 1)
+    unsigned long long timeout_ns;
 };
 
-__device__ __forceinline__ void st_word_sys(uint2* p, float v, uint32_t epoch) {
-    asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(v)), "r"(epoch) : "memory");
+__device__ __forceinline__ void st_word_sys(unsigned long long* p, unsigned long long w) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
 }
-__device__ __forceinline__ uint2 ld_word_sys(const uint2* p) {
-    uint2 w;
-    asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(w.x), "=r"(w.y) : "l"(p) : "memory");
+__device__ __forceinline__ void st_word_multicast(unsigned long long* p, unsigned long long w) {
+    asm volatile("multimem.st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_word_sys(const unsigned long long* p) {
+    unsigned long long w;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
     return w;
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
 }
 
 __global__ void __launch_bounds__(32 * kReduceSlices) allreduce_adam_kernel(ReduceArgs R, PeerArgs X, int total_chunks,
                                                                             int chunks_per_agent) {
     __shared__ float part[kReduceSlices][33];
-    __shared__ int timeout;
     __shared__ AdamBias bias;
     pdl_release();
     if (threadIdx.x == blockDim.x - 1) bias = adam_bias(X.t, R.lr);   // from launch arguments only: overlaps the predecessor's tail
     pdl_wait();
+    if (X.error[X.rank] && *reinterpret_cast<volatile int32_t*>(X.error[X.rank]) != 0) return;   // a previous exchange failed: no-op
     const int P = R.P, col = threadIdx.x & 31, slice = threadIdx.x >> 5;
     const int parity = (int)(X.epoch & 1u);
-    if (threadIdx.x == 0) timeout = 0;
     for (int c = blockIdx.x; c < total_chunks; c += gridDim.x) {
         const int n = c / chunks_per_agent, i = (c % chunks_per_agent) * 32 + col;
         float s = 0.f;
@@ -554,25 +570,46 @@ __global__ void __launch_bounds__(32 * kReduceSlices) allreduce_adam_kernel(Redu
         }
         part[slice][col] = s;
         __syncthreads();
-        if (slice == 0 && i <= P) {
+        float g = 0.f;
+        int late = 0;
+        const bool owner = slice == 0 && i <= P;
+        const int64_t idx = (int64_t)n * (P + 1) + i;
+        if (owner) {
 #pragma unroll
             for (int k = 1; k < kReduceSlices; ++k) s += part[k][col];
             if (i == P) s *= R.loss_scale;
-            const int64_t idx = (int64_t)n * (P + 1) + i;
-            const int64_t mine = X.inbox_base + ((int64_t)parity * X.world + X.rank) * X.stride + idx;
-            for (int p = 0; p < X.world; ++p) st_word_sys(X.inbox[p] + mine, s, X.epoch);   // NVLink stores (self included)
-            float g = 0.f;
+            const int64_t mine = ((int64_t)parity * X.world + X.rank) * X.stride + idx;
+            const unsigned long long word = ((unsigned long long)X.epoch << 32) | (unsigned long long)__float_as_uint(s);
+            if (X.mc_inbox) {
+                st_word_multicast(X.mc_inbox + mine, word);                                  // one store, fanned out by the switch
+            } else {
+                for (int p = 0; p < X.world; ++p) st_word_sys(X.inbox[p] + mine, word);      // NVLink stores (self included)
+            }
+            unsigned long long t_start = 0;
             for (int r = 0; r < X.world; ++r) {                              // rank order: identical sums on every rank
-                const uint2* w = X.inbox[X.rank] + X.inbox_base + ((int64_t)parity * X.world + r) * X.stride + idx;
-                uint2 m = ld_word_sys(w);
+                const unsigned long long* w = X.inbox[X.rank] + ((int64_t)parity * X.world + r) * X.stride + idx;
+                unsigned long long m = ld_word_sys(w);
                 int spins = 0;
-                while (m.y != X.epoch) {
+                while ((uint32_t)(m >> 32) != X.epoch) {
                     __nanosleep(32);
-                    if (++spins > (1 << 22)) { timeout = 1; break; }         // ~ 0.3 s: report instead of hanging
+                    if ((++spins & 63) == 0) {                               // wall-clock budget, checked every 64 polls
+                        const unsigned long long now = global_ns();
+                        if (t_start == 0) t_start = now;
+                        else if (now - t_start > X.timeout_ns) { late = 1; break; }
+                    }
                     m = ld_word_sys(w);
                 }
-                g += __uint_as_float(m.x);
+                if (late) break;
+                g += __uint_as_float((uint32_t)m);
             }
+        }
+        if (__syncthreads_or(late)) {      // block-uniform: nothing of this chunk is applied, the block stops
+            if (threadIdx.x == 0)
+                for (int p = 0; p < X.world; ++p)
+                    if (X.error[p]) asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(X.error[p]), "r"(1) : "memory");
+            return;
+        }
+        if (owner) {
             R.grad[idx] = g;
             if (i == P) {
                 R.loss_out[n] = g;
@@ -586,17 +623,7 @@ __global__ void __launch_bounds__(32 * kReduceSlices) allreduce_adam_kernel(Redu
                 adam_update(R.params[k], R.m[k], R.v[k], g, bias);
             }
         }
-        __syncthreads();
     }
-    if (threadIdx.x == 0 && timeout && X.error) *X.error = 1;
-}
-
-static void phase_regions(const ia2c_episode_desc* d, int world, int which, int64_t& inbox_base, int64_t& stride,
-                          int& chunks_per_agent) {
-    const int64_t stride_c = (int64_t)d->N * (kCriticP + 1), stride_a = (int64_t)d->N * (kActorP + 1);
-    inbox_base = which == 0 ? 0 : 2 * world * stride_c;
-    stride = which == 0 ? stride_c : stride_a;
-    chunks_per_agent = ceil_div((which == 0 ? kCriticP : kActorP) + 1, 32);
 }
 
 static int check_update_ptrs(const ia2c_episode_desc* d, const char* who) {
@@ -668,31 +695,47 @@ extern "C" int ia2c_train_episode_host(const ia2c_episode_desc* d, const float* 
 
 // ------------------------------------------------------------------------------------------------
 // Pipelined host-buffer entry point: n_episodes episodes whose injected uniforms live in (pinned) HOST
-// memory.  The H2D copy of episode k+1 runs on an internal copy stream while episode k computes; every
-// episode's losses and returns are read back to its own host slot; one host sync at the end.
-namespace {
-struct HostPipe {
+// memory.  The H2D copy of episode k+1 runs on the pipe's copy stream while episode k computes; every
+// episode's losses and returns are read back to its own host slot on the pipe's download stream; one host sync
+// at the end.  The streams and events are owned by a caller-held handle (ia2c_host_pipe_create / _destroy): the
+// library keeps no hidden per-thread state.
+struct ia2c_host_pipe {
     cudaStream_t copy = nullptr, down = nullptr;
     cudaEvent_t copied[2] = {nullptr, nullptr}, consumed[2] = {nullptr, nullptr};
     cudaEvent_t done[2] = {nullptr, nullptr}, downloaded[2] = {nullptr, nullptr};
     int device = -1;
 };
-thread_local HostPipe g_pipe;
 
-int pipe_init() {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return check_launch("cudaGetDevice");
-    if (g_pipe.copy && g_pipe.device == dev) return 0;
-    g_pipe.device = dev;
-    if (cudaStreamCreateWithFlags(&g_pipe.copy, cudaStreamNonBlocking) != cudaSuccess) return check_launch("cudaStreamCreate");
-    if (cudaStreamCreateWithFlags(&g_pipe.down, cudaStreamNonBlocking) != cudaSuccess) return check_launch("cudaStreamCreate");
-    for (int i = 0; i < 2; ++i) {
-        for (cudaEvent_t* ev : {&g_pipe.copied[i], &g_pipe.consumed[i], &g_pipe.done[i], &g_pipe.downloaded[i]})
-            if (cudaEventCreateWithFlags(ev, cudaEventDisableTiming) != cudaSuccess) return check_launch("cudaEventCreate");
-    }
+extern "C" int ia2c_host_pipe_destroy(ia2c_host_pipe* p) {
+    if (!p) return 0;
+    if (p->copy) { cudaStreamSynchronize(p->copy); cudaStreamDestroy(p->copy); }
+    if (p->down) { cudaStreamSynchronize(p->down); cudaStreamDestroy(p->down); }
+    for (int i = 0; i < 2; ++i)
+        for (cudaEvent_t ev : {p->copied[i], p->consumed[i], p->done[i], p->downloaded[i]})
+            if (ev) cudaEventDestroy(ev);
+    delete p;
+    cudaGetLastError();
     return 0;
 }
-}  // namespace
+
+extern "C" int ia2c_host_pipe_create(ia2c_host_pipe** out) {
+    IA2C_REQUIRE(out != nullptr, "ia2c_host_pipe_create: null output");
+    *out = nullptr;
+    ia2c_host_pipe* p = new ia2c_host_pipe();
+    bool ok = cudaGetDevice(&p->device) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&p->copy, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&p->down, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; i < 2 && ok; ++i)
+        for (cudaEvent_t* ev : {&p->copied[i], &p->consumed[i], &p->done[i], &p->downloaded[i]})
+            ok = ok && cudaEventCreateWithFlags(ev, cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) {
+        const int rc = check_launch("ia2c_host_pipe_create");
+        ia2c_host_pipe_destroy(p);
+        return rc ? rc : IA2C_ERR_CUDA;
+    }
+    *out = p;
+    return 0;
+}
 
 static inline size_t align8(size_t x) { return (x + 7) & ~size_t(7); }
 
@@ -708,14 +751,18 @@ extern "C" size_t ia2c_host_result_bytes(const ia2c_episode_desc* d) {
 
 // peers == nullptr: single rank (ia2c_train_episode per episode); otherwise the multi-GPU sequence with the fused
 // NVLink all-reduce + Adam after each gradient phase (desc.flags must carry SKIP_ADAM | GRAD_ONLY).
-static int episodes_host_impl(const ia2c_episode_desc* d, const ia2c_peer_desc* peers, uint32_t epoch0, void* stage_b,
-                              void* result_b, int32_t n_episodes, const void* const* host_tapes, void* host_results,
-                              void* stream) {
+static int episodes_host_impl(const ia2c_episode_desc* d, ia2c_host_pipe* pipe, const ia2c_peer_desc* peers, uint32_t epoch0,
+                              void* stage_b, void* result_b, int32_t n_episodes, const void* const* host_tapes,
+                              void* host_results, void* stream) {
     if (int rc = validate(d, "ia2c_train_episodes_host")) return rc;
     if (peers) IA2C_REQUIRE((d->flags & IA2C_FLAG_GRAD_ONLY) && (d->flags & IA2C_FLAG_SKIP_ADAM),
                             "ia2c_train_episodes_host_p2p: desc.flags must carry SKIP_ADAM | GRAD_ONLY");
     else IA2C_REQUIRE(!(d->flags & IA2C_FLAG_SKIP_ADAM), "ia2c_train_episodes_host: single-rank entry point (SKIP_ADAM set)");
+    IA2C_REQUIRE(pipe && pipe->copy && pipe->down, "ia2c_train_episodes_host: null pipe (ia2c_host_pipe_create)");
     IA2C_REQUIRE(n_episodes > 0 && host_tapes && host_results, "ia2c_train_episodes_host: null host pointer or n_episodes=%d", n_episodes);
+    int dev = -1;
+    cudaGetDevice(&dev);
+    IA2C_REQUIRE(dev == pipe->device, "ia2c_train_episodes_host: pipe was created on device %d, current device is %d", pipe->device, dev);
     const size_t n_act = (size_t)(d->T + 1) * d->E * d->N;
     const size_t off_b = align8(n_act * sizeof(float)), tape_bytes = ia2c_host_tape_bytes(d);
     const size_t off_ret = align8(2 * (size_t)d->N * sizeof(float)), res_bytes = ia2c_host_result_bytes(d);
@@ -724,59 +771,70 @@ static int episodes_host_impl(const ia2c_episode_desc* d, const ia2c_peer_desc* 
                  "ia2c_train_episodes_host: inj_u_belief must follow inj_u_action in one staging region (ia2c_host_tape_bytes)");
     IA2C_REQUIRE((const char*)d->ep_return == (const char*)d->loss_out + off_ret,
                  "ia2c_train_episodes_host: ep_return must follow loss_out in one result region (ia2c_host_result_bytes)");
-    if (int rc = pipe_init()) return rc;
     cudaStream_t s = as_stream(stream);
+    ia2c_host_pipe& g = *pipe;
     char* stage[2] = {reinterpret_cast<char*>(const_cast<float*>(d->inj_u_action)), reinterpret_cast<char*>(stage_b)};
     // with a second result region the D2H of episode k runs on its own stream while episode k+1 computes
     char* result[2] = {reinterpret_cast<char*>(d->loss_out), result_b ? reinterpret_cast<char*>(result_b) : reinterpret_cast<char*>(d->loss_out)};
-    // the copy stream must not overwrite a staging set that earlier work on `s` may still read
-    if (cudaEventRecord(g_pipe.consumed[0], s) != cudaSuccess || cudaEventRecord(g_pipe.consumed[1], s) != cudaSuccess)
-        return check_launch("cudaEventRecord");
     ia2c_episode_desc e = *d;
     const bool trace = getenv("IA2C_TRACE_HOST") != nullptr;   // diagnostics: host enqueue time vs total
     const auto t_begin = std::chrono::steady_clock::now();
-    for (int k = 0; k < n_episodes; ++k) {
-        const int b = k & 1;
-        cudaStreamWaitEvent(g_pipe.copy, g_pipe.consumed[b], 0);
-        if (cudaMemcpyAsync(stage[b], host_tapes[k], tape_bytes, cudaMemcpyHostToDevice, g_pipe.copy) != cudaSuccess)
-            return check_launch("memcpy H2D uniforms");
-        cudaEventRecord(g_pipe.copied[b], g_pipe.copy);
-        cudaStreamWaitEvent(s, g_pipe.copied[b], 0);
-        if (result_b && k >= 2) cudaStreamWaitEvent(s, g_pipe.downloaded[b], 0);   // region b was read back before it is rewritten
-        e.inj_u_action = reinterpret_cast<const float*>(stage[b]);
-        e.inj_u_belief = reinterpret_cast<const double*>(stage[b] + off_b);
-        e.loss_out = reinterpret_cast<float*>(result[b]);
-        e.ep_return = reinterpret_cast<double*>(result[b] + off_ret);
-        e.episode = d->episode + (uint32_t)k;
-        if (!peers) {
-            if (int rc = ia2c_train_episode(&e, stream)) return rc;
-        } else {
-            const int32_t adam_step = (int32_t)e.episode + 1;   // one Adam step per net per episode
-            if (int rc = ia2c_rollout(&e, stream)) return rc;
-            if (int rc = ia2c_critic_phase(&e, stream)) return rc;                                   // gradient partials only
-            if (int rc = ia2c_allreduce_adam(&e, 0, peers, epoch0 + 2 * (uint32_t)k + 1, adam_step, stream)) return rc;
-            if (int rc = ia2c_actor_phase(&e, stream)) return rc;
-            if (int rc = ia2c_allreduce_adam(&e, 1, peers, epoch0 + 2 * (uint32_t)k + 2, adam_step, stream)) return rc;
+    auto cuda_ok = [](cudaError_t err, const char* what) { return err == cudaSuccess ? 0 : check_launch(what); };
+    auto enqueue = [&]() -> int {
+        // the copy stream must not overwrite a staging set that earlier work on `s` may still read
+        if (int rc = cuda_ok(cudaEventRecord(g.consumed[0], s), "cudaEventRecord")) return rc;
+        if (int rc = cuda_ok(cudaEventRecord(g.consumed[1], s), "cudaEventRecord")) return rc;
+        for (int k = 0; k < n_episodes; ++k) {
+            const int b = k & 1;
+            cudaStreamWaitEvent(g.copy, g.consumed[b], 0);
+            if (int rc = cuda_ok(cudaMemcpyAsync(stage[b], host_tapes[k], tape_bytes, cudaMemcpyHostToDevice, g.copy), "memcpy H2D uniforms")) return rc;
+            cudaEventRecord(g.copied[b], g.copy);
+            cudaStreamWaitEvent(s, g.copied[b], 0);
+            if (result_b && k >= 2) cudaStreamWaitEvent(s, g.downloaded[b], 0);   // region b was read back before it is rewritten
+            e.inj_u_action = reinterpret_cast<const float*>(stage[b]);
+            e.inj_u_belief = reinterpret_cast<const double*>(stage[b] + off_b);
+            e.loss_out = reinterpret_cast<float*>(result[b]);
+            e.ep_return = reinterpret_cast<double*>(result[b] + off_ret);
+            e.episode = d->episode + (uint32_t)k;
+            if (!peers) {
+                if (int rc = ia2c_train_episode(&e, stream)) return rc;
+            } else {
+                const int32_t adam_step = (int32_t)e.episode + 1;   // one Adam step per net per episode
+                if (int rc = ia2c_rollout(&e, stream)) return rc;
+                if (int rc = ia2c_critic_phase(&e, stream)) return rc;                                   // gradient partials only
+                if (int rc = ia2c_allreduce_adam(&e, 0, peers, epoch0 + 2 * (uint32_t)k + 1, adam_step, stream)) return rc;
+                if (int rc = ia2c_actor_phase(&e, stream)) return rc;
+                if (int rc = ia2c_allreduce_adam(&e, 1, peers, epoch0 + 2 * (uint32_t)k + 2, adam_step, stream)) return rc;
+            }
+            cudaEventRecord(g.consumed[b], s);
+            char* host_slot = reinterpret_cast<char*>(host_results) + (size_t)k * res_bytes;
+            if (result_b) {
+                cudaEventRecord(g.done[b], s);
+                cudaStreamWaitEvent(g.down, g.done[b], 0);
+                if (int rc = cuda_ok(cudaMemcpyAsync(host_slot, result[b], res_bytes, cudaMemcpyDeviceToHost, g.down), "memcpy D2H results")) return rc;
+                cudaEventRecord(g.downloaded[b], g.down);
+            } else if (int rc = cuda_ok(cudaMemcpyAsync(host_slot, result[0], res_bytes, cudaMemcpyDeviceToHost, s), "memcpy D2H results")) {
+                return rc;
+            }
         }
-        cudaEventRecord(g_pipe.consumed[b], s);
-        char* host_slot = reinterpret_cast<char*>(host_results) + (size_t)k * res_bytes;
-        if (result_b) {
-            cudaEventRecord(g_pipe.done[b], s);
-            cudaStreamWaitEvent(g_pipe.down, g_pipe.done[b], 0);
-            if (cudaMemcpyAsync(host_slot, result[b], res_bytes, cudaMemcpyDeviceToHost, g_pipe.down) != cudaSuccess)
-                return check_launch("memcpy D2H results");
-            cudaEventRecord(g_pipe.downloaded[b], g_pipe.down);
-        } else if (cudaMemcpyAsync(host_slot, result[0], res_bytes, cudaMemcpyDeviceToHost, s) != cudaSuccess) {
-            return check_launch("memcpy D2H results");
+        if (result_b && !(n_episodes & 1)) {   // leave the last episode's results in the descriptor's own region ...
+            // ... once the download stream has finished reading region 0 (episode n-2's D2H may still be in flight)
+            cudaStreamWaitEvent(s, g.downloaded[0], 0);
+            if (int rc = cuda_ok(cudaMemcpyAsync(result[0], result[1], res_bytes, cudaMemcpyDeviceToDevice, s), "memcpy D2D results")) return rc;
         }
-    }
-    if (result_b && !(n_episodes & 1)) {   // leave the last episode's results in the descriptor's own region
-        if (cudaMemcpyAsync(result[0], result[1], res_bytes, cudaMemcpyDeviceToDevice, s) != cudaSuccess)
-            return check_launch("memcpy D2D results");
-    }
+        return 0;
+    };
+    const int rc_enqueue = enqueue();
     const auto t_enqueued = std::chrono::steady_clock::now();
-    if (cudaStreamSynchronize(s) != cudaSuccess) return check_launch("stream sync");
-    if (result_b && cudaStreamSynchronize(g_pipe.down) != cudaSuccess) return check_launch("download stream sync");
+    // drain everything that was enqueued — also on the error path, so that no copy is in flight into caller memory
+    // when this call returns
+    const cudaError_t e1 = cudaStreamSynchronize(s), e2 = cudaStreamSynchronize(g.copy), e3 = cudaStreamSynchronize(g.down);
+    if (rc_enqueue) return rc_enqueue;
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
+        set_error("ia2c_train_episodes_host: stream sync: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3)));
+        cudaGetLastError();
+        return IA2C_ERR_CUDA;
+    }
     if (trace) {
         const auto t_done = std::chrono::steady_clock::now();
         fprintf(stderr, "ia2c_train_episodes_host: %d episodes, enqueue %.1f us/episode, total %.1f us/episode\n", n_episodes,
@@ -786,16 +844,16 @@ static int episodes_host_impl(const ia2c_episode_desc* d, const ia2c_peer_desc* 
     return 0;
 }
 
-extern "C" int ia2c_train_episodes_host(const ia2c_episode_desc* d, void* stage_b, void* result_b, int32_t n_episodes,
-                                        const void* const* host_tapes, void* host_results, void* stream) {
-    return episodes_host_impl(d, nullptr, 0, stage_b, result_b, n_episodes, host_tapes, host_results, stream);
+extern "C" int ia2c_train_episodes_host(const ia2c_episode_desc* d, ia2c_host_pipe* pipe, void* stage_b, void* result_b,
+                                        int32_t n_episodes, const void* const* host_tapes, void* host_results, void* stream) {
+    return episodes_host_impl(d, pipe, nullptr, 0, stage_b, result_b, n_episodes, host_tapes, host_results, stream);
 }
 
-extern "C" int ia2c_train_episodes_host_p2p(const ia2c_episode_desc* d, const ia2c_peer_desc* peers, uint32_t epoch0,
-                                            void* stage_b, void* result_b, int32_t n_episodes,
+extern "C" int ia2c_train_episodes_host_p2p(const ia2c_episode_desc* d, ia2c_host_pipe* pipe, const ia2c_peer_desc* peers,
+                                            uint32_t epoch0, void* stage_b, void* result_b, int32_t n_episodes,
                                             const void* const* host_tapes, void* host_results, void* stream) {
     IA2C_REQUIRE(peers != nullptr, "ia2c_train_episodes_host_p2p: null peer descriptor");
-    return episodes_host_impl(d, peers, epoch0, stage_b, result_b, n_episodes, host_tapes, host_results, stream);
+    return episodes_host_impl(d, pipe, peers, epoch0, stage_b, result_b, n_episodes, host_tapes, host_results, stream);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -829,13 +887,9 @@ extern "C" int ia2c_train_episode_timed(const ia2c_episode_desc* d, float* host_
     return rc;
 }
 
-extern "C" size_t ia2c_peer_inbox_floats(const ia2c_episode_desc* d, int32_t world) {
+extern "C" size_t ia2c_peer_inbox_bytes(const ia2c_episode_desc* d, int32_t world) {
     if (!d || world < 1) return 0;
-    return (size_t)2 * 2 * world * d->N * ((kCriticP + 1) + (kActorP + 1));   // 8-byte words {value, epoch}, two parities
-}
-extern "C" size_t ia2c_peer_flag_words(const ia2c_episode_desc* d, int32_t world) {
-    if (!d || world < 1) return 0;
-    return (size_t)d->N * (ceil_div(kCriticP + 1, 32) + ceil_div(kActorP + 1, 32)) * world;
+    return (size_t)2 * world * d->N * (kCriticP + 1) * sizeof(unsigned long long);   // two parities x world slots of N*(P_max+1) words
 }
 
 extern "C" int ia2c_allreduce_adam(const ia2c_episode_desc* d, int32_t which, const ia2c_peer_desc* peers, uint32_t epoch,
@@ -848,18 +902,23 @@ extern "C" int ia2c_allreduce_adam(const ia2c_episode_desc* d, int32_t which, co
     IA2C_REQUIRE(epoch > 0 && adam_step > 0, "ia2c_allreduce_adam: epoch and adam_step start at 1");
     for (int p = 0; p < peers->world; ++p)
         IA2C_REQUIRE(peers->inbox[p] && ((uintptr_t)peers->inbox[p] & 7) == 0, "ia2c_allreduce_adam: null or misaligned peer inbox %d", p);
+    IA2C_REQUIRE(((uintptr_t)peers->mc_inbox & 7) == 0, "ia2c_allreduce_adam: misaligned multicast inbox");
     cudaStream_t s = as_stream(stream);
     ReduceArgs R = make_reduce_args(*d, which, which == 0 ? critic_partial_blocks(d) : actor_partial_blocks(d));
     R.apply_adam = 1;
     PeerArgs X;
     X.rank = peers->rank;
     X.world = peers->world;
-    for (int p = 0; p < 8; ++p) X.inbox[p] = p < peers->world ? reinterpret_cast<uint2*>(peers->inbox[p]) : nullptr;
-    X.error = peers->error;
+    for (int p = 0; p < 8; ++p) {
+        X.inbox[p] = p < peers->world ? reinterpret_cast<unsigned long long*>(peers->inbox[p]) : nullptr;
+        X.error[p] = p < peers->world ? peers->error[p] : nullptr;
+    }
+    X.mc_inbox = reinterpret_cast<unsigned long long*>(peers->mc_inbox);
     X.epoch = epoch;
     X.t = adam_step;
-    int chunks_per_agent;
-    phase_regions(d, peers->world, which, X.inbox_base, X.stride, chunks_per_agent);
+    X.stride = (int64_t)d->N * (kCriticP + 1);
+    X.timeout_ns = (unsigned long long)(peers->timeout_us ? peers->timeout_us : 2000000u) * 1000ull;
+    const int chunks_per_agent = ceil_div((which == 0 ? kCriticP : kActorP) + 1, 32);
     const int total = d->N * chunks_per_agent;
     const int grid = std::min(total, kSMs);          // persistent: every block is resident
     return launch_pdl("allreduce_adam_kernel", allreduce_adam_kernel, dim3(grid), dim3(32 * kReduceSlices), 0, s, R, X, total, chunks_per_agent);

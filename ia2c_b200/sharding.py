@@ -35,6 +35,11 @@ def global_agent_index(env_offset: int, local_env, agent, n_agents: int):
     return (env_offset + local_env) * n_agents + agent
 
 
-def global_pair_index(env_offset: int, local_env, agent, slot, n_agents: int):
-    """Philox counter of the belief stream: ((global env) * N + agent) * (N-1) + modelled-other slot."""
-    return ((env_offset + local_env) * n_agents + agent) * (n_agents - 1) + slot
+def belief_draw_index(env_offset: int, local_env, agent, slot, n_agents: int):
+    """Philox counter of the belief stream (csrc/common.cuh: philox_belief_pair; oracle/philox.py: belief_uniforms):
+    one Philox block serves TWO modelled-other slots.  For the belief row r = (global env) * N + agent with
+    K = N-1 modelled others, slots (2s, 2s+1) share the draw at index r * ceil(K/2) + s.
+    -> (draw index, word pair): pair 0 = words (x, y), pair 1 = words (z, w)."""
+    kp = n_agents // 2          # ceil((N-1)/2)
+    row = (env_offset + local_env) * n_agents + agent
+    return row * kp + slot // 2, slot % 2

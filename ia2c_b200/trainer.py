@@ -133,41 +133,62 @@ class IA2CTrainer:
     # ------------------------------------------------------------------ multi-GPU exchange
     def _setup_comm(self, comm):
         """comm="p2p": fused all-reduce + Adam kernel over NVLink peer memory (torch symmetric memory provides the
-        peer mappings, the exchange itself is ia2c_allreduce_adam); comm="nccl": reduce -> NCCL all-reduce -> Adam.
-        "auto" tries p2p and falls back to NCCL if symmetric memory cannot be set up."""
+        peer mappings, the exchange itself is ia2c_allreduce_adam; "p2p-multicast" / "p2p-unicast" force the NVSwitch
+        multicast store or the per-peer stores); comm="nccl": reduce -> NCCL all-reduce -> Adam.  "auto" tries p2p and
+        falls back to NCCL if symmetric memory cannot be set up — the decision is COLLECTIVE (all ranks or none)."""
+        import os
+
         import torch.distributed as dist
 
-        if comm in ("auto", "p2p") and self.world <= 8:
+        if comm not in ("auto", "p2p", "p2p-unicast", "p2p-multicast", "nccl"):
+            raise ValueError(f"unknown comm mode {comm!r}")
+        ok, mc_ptr, err = 0, 0, None
+        if comm != "nccl" and self.world <= 8:
             try:
                 import torch.distributed._symmetric_memory as symm
 
                 group = self.pg if self.pg is not None else dist.group.WORLD
-                n_f = int(self.lib.ia2c_peer_inbox_floats(C.byref(self.desc), self.world))
-                n_w = int(self.lib.ia2c_peer_flag_words(C.byref(self.desc), self.world))
-                self._inbox = symm.empty(n_f, dtype=torch.float32, device=self.device)
-                self._flags = symm.empty(n_w, dtype=torch.int32, device=self.device)
+                n_words = int(self.lib.ia2c_peer_inbox_bytes(C.byref(self.desc), self.world)) // 8
+                self._inbox = symm.empty(n_words, dtype=torch.int64, device=self.device)
+                self._comm_error = symm.empty(2, dtype=torch.int32, device=self.device)
                 self._inbox.zero_()
-                self._flags.zero_()
+                self._comm_error.zero_()
                 h_in = symm.rendezvous(self._inbox, group)
-                h_fl = symm.rendezvous(self._flags, group)
-                self._comm_error = torch.zeros(1, dtype=torch.int32, device=self.device)
-                self.peers = _lib.PeerDesc()
-                self.peers.rank, self.peers.world = self.rank, self.world
-                for p in range(self.world):
-                    self.peers.inbox[p] = int(h_in.buffer_ptrs[p])
-                    self.peers.flags[p] = int(h_fl.buffer_ptrs[p])
-                self.peers.error = self._comm_error.data_ptr()
-                self._symm_handles = (h_in, h_fl)
-                torch.cuda.synchronize(self.device)
-                dist.barrier(group=self.pg)      # every rank's flags are zero before anyone raises one
-                self.comm = "p2p"
-                self._epoch = 0
-                self.desc.flags |= _lib.FLAG_GRAD_ONLY
-                return
-            except Exception as exc:  # symmetric memory unavailable: NCCL path
-                if comm == "p2p":
-                    raise _lib.IA2CError(f"comm='p2p' requested but symmetric memory setup failed: {exc}") from exc
-        self.comm = "nccl"
+                h_err = symm.rendezvous(self._comm_error, group)
+                self._symm_handles = (h_in, h_err)
+                mc_ptr = int(getattr(h_in, "multicast_ptr", 0) or 0)
+                ok = 1
+            except Exception as exc:  # symmetric memory unavailable on this rank
+                err = exc
+        want_mc = comm == "p2p-multicast" or (comm in ("auto", "p2p") and os.environ.get("IA2C_P2P_MULTICAST", "0") == "1")
+        flags = torch.tensor([ok, 1 if (mc_ptr and want_mc) else 0], dtype=torch.int32, device=self.device)
+        dist.all_reduce(flags, op=dist.ReduceOp.MIN, group=self.pg)   # every rank takes the same path
+        all_ok, all_mc = (int(x) for x in flags.tolist())
+        if comm == "p2p-multicast" and all_ok and not all_mc:
+            raise _lib.IA2CError("comm='p2p-multicast' requested but the symmetric buffer has no multicast mapping on every rank")
+        if not all_ok:
+            if comm != "auto" and comm != "nccl":
+                raise _lib.IA2CError(f"comm={comm!r} requested but symmetric memory setup failed on some rank"
+                                     + (f" (this rank: {err})" if err else ""))
+            self.comm = "nccl"
+            return
+        h_in, h_err = self._symm_handles
+        self.peers = _lib.PeerDesc()
+        self.peers.rank, self.peers.world = self.rank, self.world
+        for p in range(self.world):
+            self.peers.inbox[p] = int(h_in.buffer_ptrs[p])
+            self.peers.error[p] = int(h_err.buffer_ptrs[p])
+        self.peers.mc_inbox = mc_ptr if all_mc else None
+        self.peers.timeout_us = int(os.environ.get("IA2C_P2P_TIMEOUT_US", "0"))
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.pg)      # every rank's inbox is zero (epoch 0) before anyone pushes a word
+        self.comm = "p2p-multicast" if all_mc else "p2p"
+        self._epoch = 0
+        self.desc.flags |= _lib.FLAG_GRAD_ONLY
+
+    @property
+    def p2p(self):
+        return self.comm.startswith("p2p")
 
     # ------------------------------------------------------------------ parameters
     def load_init(self, actor, critic, filter_action):
@@ -213,7 +234,7 @@ class IA2CTrainer:
     def update(self):
         d, s = C.byref(self.desc), self._stream()
         with torch.cuda.device(self.device):
-            if self.comm == "p2p":
+            if self.p2p:
                 step = self.episode + 1          # one Adam step per net per episode
                 _lib.check(self.lib.ia2c_critic_phase(d, s), "ia2c_critic_phase")      # gradient partials only
                 self._epoch += 1
@@ -303,22 +324,27 @@ class IA2CTrainer:
         self._ensure_stage()
         res_bytes = self._result_region.numel()
         if getattr(self, "_h_results", None) is None or self._h_results.shape[0] < n:
-            self._h_results = torch.zeros(n, res_bytes, dtype=torch.uint8).pin_memory()
-        if self.world > 1 and self.comm != "p2p":
+            self._h_results = torch.zeros(max(n, 64), res_bytes, dtype=torch.uint8).pin_memory()   # grows rarely: not per call
+        if self.world > 1 and not self.p2p:
             self._pipeline_multirank(host_tapes)
         else:
             ptrs = (C.c_void_p * n)(*[t.data_ptr() for t in host_tapes])
             if getattr(self, "_result_region_b", None) is None:
                 self._result_region_b = torch.zeros_like(self._result_region)
+            if getattr(self, "_pipe", None) is None:
+                handle = C.c_void_p()
+                with torch.cuda.device(self.device):
+                    _lib.check(self.lib.ia2c_host_pipe_create(C.byref(handle)), "ia2c_host_pipe_create")
+                self._pipe = handle
             self.desc.episode = self.episode
             with torch.cuda.device(self.device):
                 if self.world == 1:
-                    _lib.check(self.lib.ia2c_train_episodes_host(C.byref(self.desc), self._stage[1].data_ptr(),
+                    _lib.check(self.lib.ia2c_train_episodes_host(C.byref(self.desc), self._pipe, self._stage[1].data_ptr(),
                                                                  self._result_region_b.data_ptr(), n, ptrs,
                                                                  self._h_results.data_ptr(), self._stream()),
                                "ia2c_train_episodes_host")
                 else:   # every rank runs the same C pipeline; the gradient exchanges are the fused NVLink kernels
-                    _lib.check(self.lib.ia2c_train_episodes_host_p2p(C.byref(self.desc), C.byref(self.peers), self._epoch,
+                    _lib.check(self.lib.ia2c_train_episodes_host_p2p(C.byref(self.desc), self._pipe, C.byref(self.peers), self._epoch,
                                                                      self._stage[1].data_ptr(), self._result_region_b.data_ptr(),
                                                                      n, ptrs, self._h_results.data_ptr(), self._stream()),
                                "ia2c_train_episodes_host_p2p")
@@ -378,9 +404,21 @@ class IA2CTrainer:
         return dict(zip(("rollout", "critic_grad", "critic_reduce_adam", "actor_grad", "actor_reduce_adam"), list(ms)))
 
     def check_comm(self):
-        """Raise if a peer failed to arrive in a fused all-reduce (the kernel times out instead of hanging)."""
-        if self.comm == "p2p" and int(self._comm_error.item()):
-            raise _lib.IA2CError("ia2c_allreduce_adam: a peer rank did not arrive within the spin budget")
+        """Raise if a fused all-reduce failed anywhere in the job: a rank whose peers did not arrive within the time
+        budget applies nothing, stops exchanging and raises the error word of EVERY rank (csrc/trainer.cu), so all
+        ranks fail here together.  Called before statistics are read, before a checkpoint is taken and at the end of
+        every pipelined host call; parameters of a run that raised here must not be used."""
+        if self.p2p and int(self._comm_error[0].item()):
+            raise _lib.IA2CError("ia2c_allreduce_adam: a rank's gradient words did not arrive within the time budget; "
+                                 "the update was NOT applied and the exchange is disabled (parameters may differ across ranks)")
+
+    def __del__(self):
+        pipe, self._pipe = getattr(self, "_pipe", None), None
+        if pipe is not None:
+            try:
+                self.lib.ia2c_host_pipe_destroy(pipe)
+            except Exception:
+                pass
 
     def read_stats(self):
         self.check_comm()
@@ -419,6 +457,7 @@ class IA2CTrainer:
         state, the episode counter that keys the Philox streams, and the loss / return windows that ia2c.py prints
         (the reference has no checkpointing; SURVEY.md §5 lists this state)."""
         torch.cuda.current_stream(self.device).synchronize()
+        self.check_comm()   # never checkpoint parameters of a run whose gradient exchange failed
         sd = {k: getattr(self, k).detach().cpu().clone() for k in self._CKPT_TENSORS}
         sd.update(episode=self.episode, seed=self.seed, dims=(self.E_total, self.E, self.N, self.M, self.T),
                   rank=self.rank, world=self.world, critic_losses=list(self.critic_losses),

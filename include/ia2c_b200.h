@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define IA2C_ABI_VERSION 1
+#define IA2C_ABI_VERSION 2
 #define IA2C_HIDDEN 6          /* ac_nets.py:24 */
 #define IA2C_OBS_FEATURES 6    /* Org observation: [onehot3(prev class), onehot3(class)]  Org.py:37,112-114 */
 #define IA2C_AGENT_ACTIONS 3   /* ia2c.py:44 */
@@ -105,6 +105,12 @@ int ia2c_belief_update_pairs(uint8_t* records, const double* filter_action, cons
  * q_ieee[i] = IEEE a/b (__ddiv_rn).  Used by the tests to prove the two agree bit for bit on the
  * operand ranges the belief filter and the reward recurrence produce. */
 int ia2c_debug_divide(const double* a, const double* b, double* q_seq, double* q_ieee, int64_t n, void* stream);
+
+/* Diagnostic: the FP32 fma-pipe issue peak of this GPU — independent register-resident fma chains at full occupancy,
+ * packed != 0 with fma.rn.f32x2 (FFMA2, what csrc/mlp_f2.cuh is written in), 0 with scalar fma.rn.f32.  The measured
+ * denominator for the MLP-bound kernels (hidden_size = 6 rules tensor cores out).  out float[1] (never written in
+ * practice); host_flops_out receives the FLOPs of one launch; time it with CUDA events on `stream`. */
+int ia2c_debug_fp32_peak(float* out, int32_t iters, int32_t packed, int32_t blocks_per_sm, double* host_flops_out, void* stream);
 
 /* ------------------------------------------------------------------ (3) actor / critic MLPs -- */
 /* NeuralNet.forward (ac_nets.py:34-41) for `nets` independent networks over the same rows:
@@ -245,20 +251,27 @@ int ia2c_actor_phase(const ia2c_episode_desc* d, void* stream);
 int ia2c_apply_adam(const ia2c_episode_desc* d, int32_t which, void* stream);
 /* Multi-GPU: fused gradient all-reduce + Adam over NVLink peer memory, ONE kernel per optimiser phase instead of
  * reduce -> NCCL all-reduce -> Adam.  Run it after the phase's gradient kernel (ia2c_rollout with
- * IA2C_FLAG_FUSED_CRITIC, or ia2c_critic_phase / ia2c_actor_phase with IA2C_FLAG_SKIP_ADAM ... see trainer.py).
- * inbox[p] is rank p's symmetric buffer mapped into this process (ia2c_peer_inbox_floats floats, 8-byte aligned,
- * zero-initialised): every gradient entry travels as ONE 8-byte word {value, epoch}, so a message carries its own flag
- * (flags[] is unused and may be NULL; kept for layout compatibility).  epoch starts at 1 and increases by one per call on
- * every rank (same value on all ranks); adam_step is the Adam step number of this update.  Every rank must launch it;
- * *error is set to 1 if a peer does not arrive within the spin budget (the kernel then returns instead of hanging). */
+ * IA2C_FLAG_FUSED_CRITIC, or ia2c_critic_phase / ia2c_actor_phase with IA2C_FLAG_GRAD_ONLY).
+ * inbox[p] is rank p's symmetric buffer mapped into this process (ia2c_peer_inbox_bytes bytes, 8-byte aligned,
+ * zero-initialised): every gradient entry travels as ONE naturally aligned 64-bit word {epoch << 32 | float bits}
+ * written with a single st.relaxed.sys.u64, so a message carries its own flag and cannot tear.  mc_inbox, if not
+ * NULL, is the NVSwitch multicast mapping of the same buffers: one multimem.st then reaches every rank's inbox
+ * instead of `world` unicast stores.  epoch starts at 1 and increases by one per call on every rank (same value
+ * on all ranks); a rank can be at most one exchange ahead of a peer, so the inbox is double-buffered by epoch
+ * parity.  adam_step is the Adam step number of this update.  Every rank must launch it.
+ * Failure: if a peer's words do not arrive within timeout_us (0 -> 2 s) the kernel applies NOTHING for the
+ * affected entries, stops, and raises error[p] on EVERY rank (error[] are the ranks' symmetric int32 error
+ * words); once a rank's error word is set every later ia2c_allreduce_adam on it is a no-op.  The host must
+ * poll its own error word (trainer.py: check_comm) before trusting or checkpointing parameters. */
 typedef struct ia2c_peer_desc {
     int32_t rank, world;       /* world <= 8 (one NVSwitch domain) */
-    float* inbox[8];
-    uint32_t* flags[8];
-    int32_t* error;            /* device int32, may be NULL */
+    uint64_t* inbox[8];
+    uint64_t* mc_inbox;        /* multicast (NVLS) mapping of the inboxes, or NULL */
+    int32_t* error[8];         /* every rank's error word; error[rank] is this rank's own */
+    uint32_t timeout_us;       /* poll budget per entry in microseconds (0 -> 2 000 000) */
+    uint32_t reserved;
 } ia2c_peer_desc;
-size_t ia2c_peer_inbox_floats(const ia2c_episode_desc* d, int32_t world);
-size_t ia2c_peer_flag_words(const ia2c_episode_desc* d, int32_t world);
+size_t ia2c_peer_inbox_bytes(const ia2c_episode_desc* d, int32_t world);
 int ia2c_allreduce_adam(const ia2c_episode_desc* d, int32_t which, const ia2c_peer_desc* peers, uint32_t epoch,
                         int32_t adam_step, void* stream);
 
@@ -288,14 +301,20 @@ int ia2c_train_episode_timed(const ia2c_episode_desc* d, float* host_ms_out, voi
  * Episode numbers are desc.episode .. desc.episode + n_episodes - 1. */
 size_t ia2c_host_tape_bytes(const ia2c_episode_desc* d);
 size_t ia2c_host_result_bytes(const ia2c_episode_desc* d);
-int ia2c_train_episodes_host(const ia2c_episode_desc* d, void* stage_b, void* result_b, int32_t n_episodes,
-                             const void* const* host_tapes, void* host_results, void* stream);
+/* The pipeline's two internal streams (H2D copy, D2H download) and its events live in a caller-owned handle, created on
+ * the current device; the library keeps no hidden per-thread state.  Destroy drains and frees them. */
+typedef struct ia2c_host_pipe ia2c_host_pipe;
+int ia2c_host_pipe_create(ia2c_host_pipe** out);
+int ia2c_host_pipe_destroy(ia2c_host_pipe* pipe);
+/* On any error the call still drains everything it enqueued before returning (no copy is left in flight). */
+int ia2c_train_episodes_host(const ia2c_episode_desc* d, ia2c_host_pipe* pipe, void* stage_b, void* result_b,
+                             int32_t n_episodes, const void* const* host_tapes, void* host_results, void* stream);
 /* The same pipeline on every rank of a multi-GPU run (one process per GPU): after each gradient phase the fused NVLink
  * all-reduce + Adam (ia2c_allreduce_adam) with epochs epoch0+1 .. epoch0+2*n_episodes; desc.flags = SKIP_ADAM | GRAD_ONLY.
  * Every rank must call it with the same n_episodes. */
-int ia2c_train_episodes_host_p2p(const ia2c_episode_desc* d, const ia2c_peer_desc* peers, uint32_t epoch0, void* stage_b,
-                                 void* result_b, int32_t n_episodes, const void* const* host_tapes, void* host_results,
-                                 void* stream);
+int ia2c_train_episodes_host_p2p(const ia2c_episode_desc* d, ia2c_host_pipe* pipe, const ia2c_peer_desc* peers,
+                                 uint32_t epoch0, void* stage_b, void* result_b, int32_t n_episodes,
+                                 const void* const* host_tapes, void* host_results, void* stream);
 
 #ifdef __cplusplus
 }

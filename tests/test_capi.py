@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/ia2c_b200.h but not exported"
     assert set(names) == set(_lib.SIGNATURES), set(names) ^ set(_lib.SIGNATURES)
-    assert lib.ia2c_abi_version() == 1 and lib.ia2c_last_error() is not None
+    assert lib.ia2c_abi_version() == _lib.ABI_VERSION and lib.ia2c_last_error() is not None
 
 
 def test_episode_desc_layout_matches_c(tmp_path):

@@ -11,6 +11,7 @@ from tests.test_oracle_loops import ia2c_state_from_golden, ia2c_tapes
 
 pytestmark = pytest.mark.gpu
 RTOL = 1e-5
+_FLAG_FUSED_ROLLOUT, _FLAG_ACTOR_COLUMNS = 1, 16   # include/ia2c_b200.h
 
 
 def make_trainer(E, N, M, init, **kw):
@@ -82,16 +83,23 @@ def _compare_with_oracle(tr, st, traj, upd, N):
         assert rel_err(host(tr.actor_params)[i], st.actor[i]) < RTOL
 
 
-@pytest.mark.parametrize("E,N,M,T", [(7, 2, 5, 30), (33, 3, 5, 12), (5, 5, 3, 9), (3, 33, 5, 6), (2, 64, 5, 4)])
+@pytest.mark.parametrize("E,N,M,T", [(7, 2, 5, 30), (33, 3, 5, 12), (5, 5, 3, 9), (3, 33, 5, 6), (2, 64, 5, 4),
+                                     # N > 64: the trainer's DEFAULT kernels for the many-agent configs (cfg4 / cfg5) — env_step_kernel with
+                                     # G = 32 strided agents, actor_step_kernel, belief_pairs_table_kernel (K >= 32), critic_grad_kernel and
+                                     # the auto-selected actor_pipe_kernel — against the oracle, 256 agents = BASELINE configs[4]'s agent count
+                                     (3, 65, 5, 3), (2, 130, 5, 3), (4, 256, 5, 3)])
 def test_org_n_injected_vs_oracle(E, N, M, T):
     actor, critic, fa = _random_init(N, M, seed=E + N)
     st = L.IA2CState(actor=actor.astype(np.float64), critic=critic.astype(np.float64), filter_action=fa, T=T, max_episode_steps=T)
     tr = make_trainer(E, N, M, (actor, critic, fa), steps_per_episode=T, max_episode_steps=T)
+    if N > 64:
+        assert not (tr.desc.flags & (_FLAG_FUSED_ROLLOUT | _FLAG_ACTOR_COLUMNS))   # per-step rollout kernels + pipelined actor kernel
     rng = np.random.RandomState(N)
-    for ep in range(2):
+    for ep in range(2 if N < 256 else 1):
         actions = rng.randint(0, 3, size=(T + 1, E, N))
-        if ep == 1:
-            actions[3:6] = actions[3:6, :, :1]  # unanimous stretches hit the 6 / 5 rewards and state 0 / 4
+        if ep == 1 or N >= 256:
+            lo = 3 if T >= 6 else 1
+            actions[lo:lo + 3] = actions[lo:lo + 3, :, :1]  # unanimous stretches hit the 6 / 5 rewards and state 0 / 4
         u = rng.rand(T + 1, E, N, N - 1)
         tr.inject(actions=actions, u_belief=u)
         tr.train_episode(sync_stats=True)

@@ -5,7 +5,7 @@ import os
 import numpy as np
 import pytest
 
-from ia2c_b200.sharding import global_pair_index, shard_envs, shard_tape
+from ia2c_b200.sharding import belief_draw_index, shard_envs, shard_tape
 
 
 def test_shard_envs_and_tapes():
@@ -15,8 +15,19 @@ def test_shard_envs_and_tapes():
     tape = np.arange(31 * 8 * 2).reshape(31, 8, 2)
     parts = [shard_tape(tape, 1, r, 4) for r in range(4)]
     assert np.array_equal(np.concatenate(parts, axis=1), tape) and shard_tape(None, 1, 0, 2) is None
-    # Philox counters are global: rank 1's first local pair continues where rank 0's last one ended
-    assert global_pair_index(0, 3, 1, 0, 2) + 1 == global_pair_index(4, 0, 0, 0, 2)
+    # Philox counters are global: rank 1's first belief row continues where rank 0's last one ended, and the layout is
+    # the one the oracle's generator (which mirrors the kernels) uses: slots (2s, 2s+1) of row r share draw r*ceil(K/2)+s
+    for n_agents in (2, 3, 5, 64):
+        kp = n_agents // 2
+        last = belief_draw_index(0, 3, n_agents - 1, n_agents - 2, n_agents)
+        first = belief_draw_index(4, 0, 0, 0, n_agents)
+        assert first == (last[0] + 1, 0) and last[0] == (4 * n_agents - 1) * kp + (n_agents - 2) // 2
+    from oracle import philox as P
+    rows = np.array([[5 * 3 + 1]])                                  # env 5, agent 1 of N=3 (K=2: one draw, two word pairs)
+    u = P.belief_uniforms(9, 2, 7, rows, 2)
+    idx, pair = belief_draw_index(4, 1, 1, 1, 3)                    # rank offset 4 + local env 1 = global env 5, slot 1
+    x = P.draw(9, P.STREAM_BELIEF, 2, 7, np.array([idx]))
+    assert pair == 1 and u[0, 0, 1] == P._unit_f64(x[2], x[3])[0]
 
 
 def _worker(rank, world, port, E, out):
