@@ -89,6 +89,7 @@ SIGNATURES = {
     "ia2c_peer_inbox_bytes": (C.c_size_t, [_DP, i32]),
     "ia2c_allreduce_adam": (C.c_int, [_DP, i32, C.POINTER(PeerDesc), u32, i32, vp]),
     "ia2c_train_episode": (C.c_int, [_DP, vp]),
+    "ia2c_train_episode_p2p": (C.c_int, [_DP, C.POINTER(PeerDesc), u32, vp]),
     "ia2c_train_episode_host": (C.c_int, [_DP, vp, vp, vp, vp, vp]),
     "ia2c_train_episode_timed": (C.c_int, [_DP, vp, vp]),
     "ia2c_host_tape_bytes": (C.c_size_t, [_DP]),

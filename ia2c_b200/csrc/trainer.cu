@@ -667,6 +667,20 @@ extern "C" int ia2c_train_episode(const ia2c_episode_desc* d, void* stream) {
     return ia2c_actor_phase(d, stream);
 }
 
+// One episode of a multi-GPU run in ONE call per rank: rollout, critic gradient, fused NVLink all-reduce + Adam
+// (epoch0 + 1), actor gradient, fused all-reduce + Adam (epoch0 + 2).  desc.flags = SKIP_ADAM | GRAD_ONLY.
+extern "C" int ia2c_train_episode_p2p(const ia2c_episode_desc* d, const ia2c_peer_desc* peers, uint32_t epoch0, void* stream) {
+    IA2C_REQUIRE(d && peers, "ia2c_train_episode_p2p: null descriptor");
+    IA2C_REQUIRE((d->flags & IA2C_FLAG_GRAD_ONLY) && (d->flags & IA2C_FLAG_SKIP_ADAM),
+                 "ia2c_train_episode_p2p: desc.flags must carry SKIP_ADAM | GRAD_ONLY");
+    const int32_t adam_step = (int32_t)d->episode + 1;   // one Adam step per net per episode
+    if (int rc = ia2c_rollout(d, stream)) return rc;
+    if (int rc = ia2c_critic_phase(d, stream)) return rc;
+    if (int rc = ia2c_allreduce_adam(d, 0, peers, epoch0 + 1, adam_step, stream)) return rc;
+    if (int rc = ia2c_actor_phase(d, stream)) return rc;
+    return ia2c_allreduce_adam(d, 1, peers, epoch0 + 2, adam_step, stream);
+}
+
 extern "C" int ia2c_train_episode_host(const ia2c_episode_desc* d, const float* host_u_action,
                                        const double* host_u_belief, float* host_loss_out, double* host_ep_return,
                                        void* stream) {
@@ -799,12 +813,7 @@ static int episodes_host_impl(const ia2c_episode_desc* d, ia2c_host_pipe* pipe, 
             if (!peers) {
                 if (int rc = ia2c_train_episode(&e, stream)) return rc;
             } else {
-                const int32_t adam_step = (int32_t)e.episode + 1;   // one Adam step per net per episode
-                if (int rc = ia2c_rollout(&e, stream)) return rc;
-                if (int rc = ia2c_critic_phase(&e, stream)) return rc;                                   // gradient partials only
-                if (int rc = ia2c_allreduce_adam(&e, 0, peers, epoch0 + 2 * (uint32_t)k + 1, adam_step, stream)) return rc;
-                if (int rc = ia2c_actor_phase(&e, stream)) return rc;
-                if (int rc = ia2c_allreduce_adam(&e, 1, peers, epoch0 + 2 * (uint32_t)k + 2, adam_step, stream)) return rc;
+                if (int rc = ia2c_train_episode_p2p(&e, peers, epoch0 + 2 * (uint32_t)k, stream)) return rc;
             }
             cudaEventRecord(g.consumed[b], s);
             char* host_slot = reinterpret_cast<char*>(host_results) + (size_t)k * res_bytes;

@@ -263,6 +263,12 @@ class IA2CTrainer:
             self.desc.episode = self.episode
             with torch.cuda.device(self.device):
                 _lib.check(self.lib.ia2c_train_episode(C.byref(self.desc), self._stream()), "ia2c_train_episode")
+        elif self.p2p:        # one C call per rank: the gradient exchanges are kernels of the same stream
+            self.desc.episode = self.episode
+            with torch.cuda.device(self.device):
+                _lib.check(self.lib.ia2c_train_episode_p2p(C.byref(self.desc), C.byref(self.peers), self._epoch, self._stream()),
+                           "ia2c_train_episode_p2p")
+            self._epoch += 2
         else:
             self.rollout()
             self.update()

@@ -274,6 +274,11 @@ typedef struct ia2c_peer_desc {
 size_t ia2c_peer_inbox_bytes(const ia2c_episode_desc* d, int32_t world);
 int ia2c_allreduce_adam(const ia2c_episode_desc* d, int32_t which, const ia2c_peer_desc* peers, uint32_t epoch,
                         int32_t adam_step, void* stream);
+/* One whole episode of a multi-GPU run in one call per rank: ia2c_rollout, critic gradient, ia2c_allreduce_adam
+ * (epoch0 + 1), actor gradient, ia2c_allreduce_adam (epoch0 + 2); Adam step number = desc.episode + 1.
+ * desc.flags must carry SKIP_ADAM | GRAD_ONLY.  The caller advances its epoch counter by 2. */
+int ia2c_train_episode_p2p(const ia2c_episode_desc* d, const ia2c_peer_desc* peers, uint32_t epoch0, void* stream);
+
 
 /* rollout + critic phase + actor phase on one stream. */
 int ia2c_train_episode(const ia2c_episode_desc* d, void* stream);

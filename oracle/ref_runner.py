@@ -82,10 +82,12 @@ def _threads():
     return dict(torch_threads=torch.get_num_threads(), blas_threads=blas, host_logical_cpus=os.cpu_count())
 
 
-def time_ia2c(n_envs, warmup, episodes, seed=0):
+def time_ia2c(n_envs, warmup, episodes, seed=0, warm_envs=0):
     """The reference's own ia2c.py main block (ia2c.py:41-134) at ``n_envs`` envs for warmup+episodes episodes.
     Episode boundaries are the script's ``envs.reset()`` calls (ia2c.py:72), time-stamped by a hook on the
-    stand-in vector env (the fixture, not the reference).  -> dict with per-episode seconds of the timed part."""
+    stand-in vector env (the fixture, not the reference).  ``warm_envs`` > 0 first runs the script once for one
+    small episode (torch's lazy initialisation) so that a bounded run needs fewer full-size warm-up episodes.
+    -> dict with per-episode seconds of the timed part."""
     import numpy as np
     import torch
 
@@ -102,6 +104,8 @@ def time_ia2c(n_envs, warmup, episodes, seed=0):
         stamps.append(time.perf_counter())
         return v_reset(self_, *a, **k)
 
+    if warm_envs:
+        run_script(ref, "ia2c.py", [(r"^NUM_EPISODES = \d+", "NUM_EPISODES = 1"), (r"^n_envs=\d+", f"n_envs={int(warm_envs)}")])
     gym_standin.SyncVectorEnv.reset = stamped_reset
     try:
         torch.manual_seed(seed)
@@ -202,12 +206,13 @@ def main():
     ap.add_argument("--rows-t", type=int, default=64)
     ap.add_argument("--rows-e", type=int, default=1024)
     ap.add_argument("--features", type=int, default=500)
+    ap.add_argument("--warm-envs", type=int, default=0)
     a = ap.parse_args()
     if a.what == "all":   # one interpreter (one torch import) for the three CPU legs bench.py reports
-        r = dict(ia2c=time_ia2c(a.envs, a.warmup, a.episodes), a2c_org=time_a2c_org(2, 10),
+        r = dict(ia2c=time_ia2c(a.envs, a.warmup, a.episodes, warm_envs=a.warm_envs), a2c_org=time_a2c_org(2, 10),
                  acnets=time_acnets(a.rows_t, a.rows_e, a.features, 6, 6, 1, 3))
     elif a.what == "ia2c":
-        r = time_ia2c(a.envs, a.warmup, a.episodes)
+        r = time_ia2c(a.envs, a.warmup, a.episodes, warm_envs=a.warm_envs)
     elif a.what == "a2c_org":
         r = time_a2c_org(a.warmup, a.episodes)
     else:

@@ -1,4 +1,5 @@
-"""bench.py contract checks that need no GPU: the reference arm (CPU, oracle port) prints one JSON line with the agreed keys."""
+"""bench.py contract checks that need no GPU: the reference arm (the unmodified reference loop from baseline/_ref on the host CPU,
+or the oracle port when the staged copy is absent) prints one JSON line with the agreed keys."""
 import json
 import os
 import subprocess
@@ -9,12 +10,14 @@ from tests.conftest import ROOT
 
 def test_reference_arm_json_line():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1",
-                        "--cpu-sample-envs", "64"], capture_output=True, text=True, timeout=600)
+                        "--cpu-envs", "64"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     line = json.loads(r.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "agent-steps/s" and line["higher_is_better"] is True
     assert line["metric"].startswith("agent-steps/sec") and line["value"] > 0 and line["steps"] == 2
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and "sample" in line["cpu_baseline"]
+    have_ref = os.path.exists(os.path.join(ROOT, "baseline", "_ref", "MANIFEST.json"))
+    assert line["cpu_baseline"]["kind"] == ("reference" if have_ref else "port")
+    assert line["cpu_baseline"]["cores"] >= 1 and "sample" in line["cpu_baseline"] and line["warmup"] == 1
     assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in line["config"] and "model" not in line["config"]
 
