@@ -75,7 +75,7 @@ def med_spread(xs):
 class ClockSampler:
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-              "clocks_event_reasons.sw_power_cap")
+              "clocks_event_reasons.sw_power_cap,pcie.link.gen.current,pcie.link.width.current")
 
     def __init__(self, index):
         self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
@@ -107,7 +107,7 @@ class ClockSampler:
             parts = [p.strip() for p in line.split(",")]
             if len(parts) >= 7:
                 try:
-                    rows.append((float(parts[0]), float(parts[1]), parts[3:7]))
+                    rows.append((float(parts[0]), float(parts[1]), parts[3:7], parts[7:9]))
                 except ValueError:
                     pass
         os.unlink(self.tmp.name)
@@ -119,7 +119,9 @@ class ClockSampler:
         sm = sorted(r[0] for r in load)
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({names[i] for r in load for i in range(4) if r[2][i].lower().startswith("active")})
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(r[1] for r in load), "reasons": reasons, "samples": len(load)}
+        pcie = sorted({"gen" + "x".join(r[3]) for r in load if len(r[3]) == 2})
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(r[1] for r in load), "reasons": reasons, "samples": len(load),
+                "pcie_link_seen": pcie}
 
 
 # ------------------------------------------------------------------------------------------ CPU legs
@@ -526,7 +528,11 @@ def bench_headline(ctx, args, _lib, peak_gbs, peak_src, sampler):
             tr.train_episodes_host([tapes[(done + j) % n_bufs] for j in range(m)])
             done += m
 
-    e2e_run(K)   # warm-up with the SAME n: every buffer the timed call touches already exists
+    # warm-up with the SAME n (every buffer the timed call touches already exists) and for long enough that the PCIe link
+    # has left its idle power state: the first tens of milliseconds of copies after a compute-only phase run at 10-20 GB/s
+    # instead of ~50 GB/s (tools/e2e_probe.py, profiles/r02_e2e.md)
+    for _ in range(max(1, -(-4000 // K))):
+        e2e_run(K)
     e2e_blocks, e2e_wall = [], []
     for r in range(R):
         ctx.barrier()

@@ -794,6 +794,12 @@ static int episodes_host_impl(const ia2c_episode_desc* d, ia2c_host_pipe* pipe, 
     const bool trace = getenv("IA2C_TRACE_HOST") != nullptr;   // diagnostics: host enqueue time vs total
     const auto t_begin = std::chrono::steady_clock::now();
     auto cuda_ok = [](cudaError_t err, const char* what) { return err == cudaSuccess ? 0 : check_launch(what); };
+    // trace only: timing events around every H2D copy (copy stream) and every episode's kernels (compute stream)
+    constexpr int kTraceMax = 64;
+    cudaEvent_t tr_ev[kTraceMax][4] = {};
+    const int n_traced = trace ? std::min<int>(n_episodes, kTraceMax) : 0;
+    for (int k = 0; k < n_traced; ++k)
+        for (int j = 0; j < 4; ++j) cudaEventCreate(&tr_ev[k][j]);
     auto enqueue = [&]() -> int {
         // the copy stream must not overwrite a staging set that earlier work on `s` may still read
         if (int rc = cuda_ok(cudaEventRecord(g.consumed[0], s), "cudaEventRecord")) return rc;
@@ -801,7 +807,9 @@ static int episodes_host_impl(const ia2c_episode_desc* d, ia2c_host_pipe* pipe, 
         for (int k = 0; k < n_episodes; ++k) {
             const int b = k & 1;
             cudaStreamWaitEvent(g.copy, g.consumed[b], 0);
+            if (k < n_traced) cudaEventRecord(tr_ev[k][0], g.copy);
             if (int rc = cuda_ok(cudaMemcpyAsync(stage[b], host_tapes[k], tape_bytes, cudaMemcpyHostToDevice, g.copy), "memcpy H2D uniforms")) return rc;
+            if (k < n_traced) cudaEventRecord(tr_ev[k][1], g.copy);
             cudaEventRecord(g.copied[b], g.copy);
             cudaStreamWaitEvent(s, g.copied[b], 0);
             if (result_b && k >= 2) cudaStreamWaitEvent(s, g.downloaded[b], 0);   // region b was read back before it is rewritten
@@ -810,11 +818,13 @@ static int episodes_host_impl(const ia2c_episode_desc* d, ia2c_host_pipe* pipe, 
             e.loss_out = reinterpret_cast<float*>(result[b]);
             e.ep_return = reinterpret_cast<double*>(result[b] + off_ret);
             e.episode = d->episode + (uint32_t)k;
+            if (k < n_traced) cudaEventRecord(tr_ev[k][2], s);
             if (!peers) {
                 if (int rc = ia2c_train_episode(&e, stream)) return rc;
             } else {
                 if (int rc = ia2c_train_episode_p2p(&e, peers, epoch0 + 2 * (uint32_t)k, stream)) return rc;
             }
+            if (k < n_traced) cudaEventRecord(tr_ev[k][3], s);
             cudaEventRecord(g.consumed[b], s);
             char* host_slot = reinterpret_cast<char*>(host_results) + (size_t)k * res_bytes;
             if (result_b) {
@@ -845,6 +855,22 @@ static int episodes_host_impl(const ia2c_episode_desc* d, ia2c_host_pipe* pipe, 
         return IA2C_ERR_CUDA;
     }
     if (trace) {
+        double copy_ms = 0, comp_ms = 0;
+        for (int k = 0; k < n_traced; ++k) {
+            float a = 0, b = 0, c0 = 0, c1 = 0;
+            cudaEventElapsedTime(&a, tr_ev[k][0], tr_ev[k][1]);
+            cudaEventElapsedTime(&b, tr_ev[k][2], tr_ev[k][3]);
+            cudaEventElapsedTime(&c0, tr_ev[0][0], tr_ev[k][0]);   // copy start / compute start relative to the first copy
+            cudaEventElapsedTime(&c1, tr_ev[0][0], tr_ev[k][2]);
+            copy_ms += a;
+            comp_ms += b;
+            if (k < 8 || k >= n_traced - 2)
+                fprintf(stderr, "  episode %2d: H2D starts %8.1f us, takes %6.1f us; kernels start %8.1f us, take %6.1f us\n", k, c0 * 1e3, a * 1e3,
+                        c1 * 1e3, b * 1e3);
+        }
+        if (n_traced) fprintf(stderr, "  mean H2D %.1f us, mean kernels %.1f us per episode\n", copy_ms * 1e3 / n_traced, comp_ms * 1e3 / n_traced);
+        for (int k = 0; k < n_traced; ++k)
+            for (int j = 0; j < 4; ++j) cudaEventDestroy(tr_ev[k][j]);
         const auto t_done = std::chrono::steady_clock::now();
         fprintf(stderr, "ia2c_train_episodes_host: %d episodes, enqueue %.1f us/episode, total %.1f us/episode\n", n_episodes,
                 std::chrono::duration<double, std::micro>(t_enqueued - t_begin).count() / n_episodes,
