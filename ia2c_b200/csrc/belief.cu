@@ -146,6 +146,8 @@ struct PairsArgs {
     int N, K, envs_per_block, agents_per_block, chunks_per_env, reset_prior;
     uint64_t seed;
     uint32_t episode, t;
+    uint32_t rk[20];               // Philox round keys (k0_r, k1_r), r = 0..9 — derived from seed on the host so that the
+                                   // rounds read them straight from the constant bank (table kernel)
 };
 
 template <int M>
@@ -237,48 +239,123 @@ __global__ void debug_divide_kernel(const double* __restrict__ a, const double* 
 // ------------------------------------------------------------------------------------------------
 // Table-driven pairwise update for many modelled others (K >= 32).
 //
-// belief_pairs_kernel is bound by the fp64 pipe (~100 DP instructions per record against 16 B of traffic).  Two
-// observations remove two thirds of them without changing a single output bit:
+// belief_pairs_kernel costs ~100 fp64 instructions per record against 16 B of traffic.  This kernel keeps every
+// output bit and spends ~1/3 of the instructions, none of them fp64 on the common path:
 //  (1) the un-normalised posterior bp[m] = (l0*(F[m][0]*p) + l1*(F[m][1]*p)) + l2*(F[m][2]*p) depends only on the
 //      agent's model m, the SEEN action (3 likelihood rows) and the prior, which is k/100 with integer k in 0..100.
-//      A block that owns ONE agent therefore tabulates all 3*M*101 values once (same fp64 operations, same
-//      order) and each record needs M table lookups instead of 6M multiply/adds;
-//  (2) the mixture prediction is only COMPARED with u.  It is evaluated in fp32 (a different pipe); when u lies
-//      within 1e-5 of a decision boundary — the fp32 error is below 1e-6 — the record falls back to the exact
-//      fp64 sequence.  The fallback rate is ~6e-5 per record;
-//  (3) the posterior is stored rounded to hundredths, so the M IEEE divisions are replaced by multiplications with the
-//      shared reciprocal plus a fixed-point test that proves the rounding agrees (exact fallback otherwise).
-// Per record that leaves S, one shared reciprocal, M corrected divisions and M roundings on the fp64 pipe.
-// Block = (agent i, chunk of envs): the agent's K records of one env are 8*K contiguous bytes.
+//      A block that owns ONE agent tabulates all 3*M*101 values once in fp64 (same operations, same order as
+//      belief_core) and keeps an fp32 copy of the table;
+//  (2) the stored posterior is rint(100 * bp[m]/S) and the predicted action is a comparison of u with the cumulative
+//      mixture — both are DECISIONS, so they are first taken in fp32 (table lookups, one MUFU.RCP, FFMA) together with
+//      a rigorous distance-to-the-boundary test: the fp32 quotient 100*bp/S is within 6e-5 of the fp64 value
+//      (9 roundings of 2^-24 relative on a value <= 100), so a rounding is accepted only when it is more than 2.5e-4
+//      away from a half-integer; the inverse-CDF comparison u*S < sum_m bp[m]*Fcum[m][a] is accepted only when the
+//      two sides differ by more than 1e-5*S (their fp32 errors are below 1e-6*S each);
+//  (3) a record that fails either test (~0.3 % of them) is recomputed with the exact fp64 sequence of belief_core on
+//      the fp64 table (same operands, same order, IEEE division) — bit-identical to belief_pairs_kernel and to the
+//      oracle by construction, and checked against both by tests/test_gpu_belief.py.
+// Thread = the FOUR modelled-other slots 4s..4s+3 of one (env, agent): they share one Philox block (common.cuh:
+// philox_belief_quad) and give the scheduler four independent chains; the agent's K records of one env are 8*K
+// contiguous bytes.  The per-agent predicted-action counts are packed 3 x 10 bits and reduced with one warp REDUX +
+// one shared-memory atomic per (warp, env) instead of one atomic per record.
 // FAST = the steady-state call of the rollout (device Philox, no dumps, priors from the records): the optional
 // pointers are compiled out instead of costing a predicated-off instruction each per record.
+constexpr float kRoundMagic = 12582912.f;       // 1.5 * 2^23: x + magic has rint(x) in its low mantissa bits
+constexpr float kHalfWindow = 0.5f - 2.5e-4f;    // |100*b - rint(100*b)| above this -> exact path
+constexpr float kCdfWindow = 1e-5f;              // |u*S - cumulative| below this * S -> exact path
+
+template <int M>
+struct TableView {
+    const double* bpt;     // [A][M][101] fp64 un-normalised posteriors
+    const float* bpt32;    // the same in fp32
+    const double* fa;      // [M][A]
+};
+
+// exact fp64 sequence (belief_core on the table): -> the packed record {posterior hundredths, predicted action in byte 6}
+template <int M>
+__device__ __noinline__ uint2 belief_exact_record(const double* __restrict__ row, const double* __restrict__ fa, uint2 raw, int prior_k,
+                                                  double u) {
+    constexpr int A = IA2C_AGENT_ACTIONS;
+    double bp[M], b[M];
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+        const uint32_t word = m < 4 ? raw.x : raw.y;
+        const int k = prior_k >= 0 ? prior_k : (int)((word >> (8 * (m & 3))) & 0xFFu);
+        bp[m] = row[m * 101 + k];
+    }
+    double S = bp[0];
+#pragma unroll
+    for (int m = 1; m < M; ++m) S = __dadd_rn(S, bp[m]);
+    const double rS = drcp_seq(S);
+    uint32_t lo = 0, hi = 0;
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+        b[m] = ddiv_with(bp[m], S, rS);
+        const uint32_t k = (uint32_t)__double2int_rn(__dmul_rn(b[m], 100.0));
+        if (m < 4) lo |= k << (8 * m); else hi |= k << (8 * (m - 4));
+    }
+    double c = 0.0;
+    int ap = 0;
+    bool found = false;
+#pragma unroll
+    for (int a = 0; a < A; ++a) {
+        double acc = 0.0;
+#pragma unroll
+        for (int m = 0; m < M; ++m) acc = __dadd_rn(acc, __dmul_rn(b[m], fa[m * A + a]));
+        c = (a == 0) ? acc : __dadd_rn(c, acc);
+        if (!found && u < c) { ap = a; found = true; }
+    }
+    return make_uint2(lo, hi | ((uint32_t)ap << 16));
+}
+
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+    float v;
+    asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+
+// Philox4x32-10 with precomputed round keys (identical to philox4x32_10: key_r = key_0 + r * W)
+__device__ __forceinline__ uint4 philox4x32_10_rk(uint4 c, const uint32_t (&rk)[20]) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ rk[2 * r], lo1, hi0 ^ c.w ^ rk[2 * r + 1], lo0);
+    }
+    return c;
+}
+
+constexpr int kExactQueue = 1024;   // deferred exact-path records per block (expected ~0.25 % of <= 32640; overflow -> inline)
+
 template <int M, bool FAST>
-__global__ void __launch_bounds__(kThreads, 4) belief_pairs_table_kernel(PairsArgs P) {
+__global__ void __launch_bounds__(kThreads, 2) belief_pairs_table_kernel(const __grid_constant__ PairsArgs P) {
     constexpr int A = IA2C_AGENT_ACTIONS;
     const bool reset_prior = !FAST && P.reset_prior;
     const double* const u_injected = FAST ? nullptr : P.u_injected;
     uint8_t* const belief_out = FAST ? nullptr : P.belief_out;
     uint8_t* const pred_out = FAST ? nullptr : P.pred_out;
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int queue_n;
     const int N = P.N, K = P.K, i = blockIdx.y;
+    const int KQ = (K + 3) >> 2;                                     // quads per (env, agent); K padded to whole quads
     const int EC = P.envs_per_block;
     const int64_t e0 = (int64_t)blockIdx.x * EC;
     const int n_envs = (int)min((int64_t)EC, P.E - e0);
-    double* tab = reinterpret_cast<double*>(smem_raw);              // [104]   k/100
-    double* bpt = tab + 104;                                        // [A][M][101]
-    double* fa = bpt + A * M * 101;                                 // [M][A]
-    float* fa32 = reinterpret_cast<float*>(fa + M * A);             // [M][A]
-    int* counts = reinterpret_cast<int*>(fa32 + ((M * A + 3) & ~3)); // [EC][A]
-    uint8_t* act = reinterpret_cast<uint8_t*>(counts + EC * A);     // [EC][N]
+    double* tab = reinterpret_cast<double*>(smem_raw);               // [104]   k/100
+    double* bpt = tab + 104;                                         // [A][M][101]
+    double* fa = bpt + A * M * 101;                                  // [M][A]
+    float* bpt32 = reinterpret_cast<float*>(fa + M * A);             // [A][M][101]
+    float* fcum = bpt32 + ((A * M * 101 + 3) & ~3);                  // [2][M]: F[m][0], F[m][0]+F[m][1]
+    uint32_t* counts = reinterpret_cast<uint32_t*>(fcum + ((2 * M + 3) & ~3));   // [EC] packed 3 x 10 bits
+    uint16_t* queue = reinterpret_cast<uint16_t*>(counts + EC);      // [kExactQueue] deferred records: 4 * quad + slot
+    uint32_t* seen4 = reinterpret_cast<uint32_t*>(queue + kExactQueue);   // [EC][KQ]: the OTHERS' actions, 4 slots per word
     pdl_release();
     // the table depends only on the agent's models: it is built while the kernel that samples this step's actions
     // may still be running (programmatic dependent launch); pdl_wait() below orders the reads of its output
     for (int k = threadIdx.x; k <= 100; k += blockDim.x) tab[k] = __ddiv_rn((double)k, 100.0);
-    for (int k = threadIdx.x; k < M * A; k += blockDim.x) {
-        fa[k] = P.filter_action[(int64_t)i * M * A + k];
-        fa32[k] = (float)fa[k];
-    }
-    for (int k = threadIdx.x; k < n_envs * A; k += blockDim.x) counts[k] = 0;
+    for (int k = threadIdx.x; k < M * A; k += blockDim.x) fa[k] = P.filter_action[(int64_t)i * M * A + k];
+    for (int k = threadIdx.x; k < n_envs; k += blockDim.x) counts[k] = 0u;
+    if (threadIdx.x == 0) queue_n = 0;
     __syncthreads();
     for (int x = threadIdx.x; x < A * M * 101; x += blockDim.x) {
         const int seen = x / (M * 101), m = (x / 101) % M, k = x % 101;
@@ -287,147 +364,248 @@ __global__ void __launch_bounds__(kThreads, 4) belief_pairs_table_kernel(PairsAr
 #pragma unroll
         for (int a = 1; a < A; ++a) acc = __dadd_rn(acc, __dmul_rn(seen == a ? 0.8 : 0.1, __dmul_rn(fa[m * A + a], p)));
         bpt[x] = acc;
+        bpt32[x] = (float)acc;
+    }
+    if (threadIdx.x < M) {
+        fcum[threadIdx.x] = (float)fa[threadIdx.x * A];
+        fcum[M + threadIdx.x] = (float)__dadd_rn(fa[threadIdx.x * A], fa[threadIdx.x * A + 1]);
     }
     pdl_wait();
-    for (int k = threadIdx.x; k < n_envs * N; k += blockDim.x) act[k] = P.actions[e0 * N + k];
+    // the others' actions of every env of the block, own action skipped, padded to whole quads: slot jj of env el is
+    // byte jj of word el*KQ + jj/4, so a thread's four slots are ONE 32-bit shared load.  Word w of a row is the source
+    // word w (slots below i), the source bytes 4w+1..4w+4 (slots above i), or a mix (the word that contains i).
+    if ((N & 3) == 0) {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(P.actions + e0 * N);   // rows are 4-byte aligned (N % 4 == 0)
+        const int NW = N >> 2, iw = i >> 2;
+        const uint32_t sel_mix = (i & 3) == 0 ? 0x4321u : ((i & 3) == 1 ? 0x4320u : ((i & 3) == 2 ? 0x4310u : 0x4210u));
+        const int words = n_envs * KQ;
+#pragma unroll 4
+        for (int x = threadIdx.x; x < words; x += blockDim.x) {
+            const int el = x / KQ, w = x - el * KQ;
+            const uint32_t lo = src[el * NW + w];
+            const uint32_t hi = (w + 1 < NW) ? src[el * NW + w + 1] : 0u;
+            uint32_t v = __byte_perm(lo, hi, w < iw ? 0x3210u : (w > iw ? 0x4321u : sel_mix));
+            if (4 * w + 3 >= K) v &= 0xFFFFFFFFu >> (8 * (4 * w + 4 - K));      // zero the padding slots
+            seen4[x] = v;
+        }
+    } else {
+        uint8_t* seen_b = reinterpret_cast<uint8_t*>(seen4);
+        const int KP = 4 * KQ;
+        for (int x = threadIdx.x; x < n_envs * KP; x += blockDim.x) {
+            const int el = x / KP, jj = x - el * KP;
+            seen_b[x] = jj < K ? P.actions[(e0 + el) * N + jj + (jj >= i)] : (uint8_t)0;
+        }
+    }
     __syncthreads();
-    const int prior_k = (int)rint(100.0 / M);
-    // One thread = one PAIR of modelled-other slots (2s, 2s+1) of one env: the two records share a Philox block and
-    // give the scheduler two independent chains.
-    const int KP = (K + 1) >> 1;
-    const float inv_kp = 1.f / (float)KP;
-    const int total = n_envs * KP;
-    auto one_record = [&](int64_t rec, int el, int jj, double u, uint2 raw) -> int {
-        const int j = jj + (jj >= i);
-        const double* row = bpt + act[el * N + j] * (M * 101);
-        double bp[M];
+    const int prior_k = reset_prior ? (int)rint(100.0 / M) : -1;
+    float f0[M], f01[M];
+#pragma unroll
+    for (int m = 0; m < M; ++m) { f0[m] = fcum[m]; f01[m] = fcum[M + m]; }
+    const uint32_t bpt32_s = (uint32_t)__cvta_generic_to_shared(bpt32);   // explicit shared-window addresses for the lookups
+
+    // fp32 screen of one record -> the packed record {posterior hundredths, predicted action in byte 6}; `exact` is set
+    // when a rounding or the inverse-CDF decision is too close to call in fp32
+    auto screen_record = [&](uint32_t seen, float uf, uint2 raw, bool& exact) -> uint2 {
+        const uint32_t row = bpt32_s + seen * (M * 101 * 4);
+        float bp[M];
 #pragma unroll
         for (int m = 0; m < M; ++m) {
-            const uint32_t word = m < 4 ? raw.x : raw.y;
-            const int k = reset_prior ? prior_k : (int)((word >> (8 * (m & 3))) & 0xFFu);
-            bp[m] = row[m * 101 + k];
+            const uint32_t k = reset_prior ? (uint32_t)prior_k : __byte_perm(m < 4 ? raw.x : raw.y, 0u, 0x4440u | (uint32_t)(m & 3));
+            bp[m] = lds_f32(row + 4u * k + (uint32_t)(m * 101 * 4));
         }
-        double S = bp[0];
+        float S = bp[0];
 #pragma unroll
-        for (int m = 1; m < M; ++m) S = __dadd_rn(S, bp[m]);
-        const double rS = drcp_seq(S);
-        // (3) screened quotients: q~ = bp * (1/S) is within 4e-16 of the IEEE quotient b = bp / S, and the posterior is
-        //     only used ROUNDED to hundredths: z = rint(q~ * 100 * 2^20) is 100*b in fixed point, exact to 1e-6; unless
-        //     its fraction is within 2^-19 of one half, rint(100*q~) == rint(100*b) and the M divisions are skipped.
-        uint32_t kq[M];
-        float bf[M];
-        bool near_half = false;
+        for (int m = 1; m < M; ++m) S += bp[m];
+        float r;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(S));
+        const float r100 = r * 100.f;
+        uint32_t kb[M];
+        float dmax = 0.f;
 #pragma unroll
         for (int m = 0; m < M; ++m) {
-            const double qa = __dmul_rn(bp[m], rS);
-            const int z = __double2int_rn(__dmul_rn(qa, 104857600.0));   // 100 * 2^20, exact scaling
-            bf[m] = (float)qa;
-            kq[m] = (uint32_t)(z + (1 << 19)) >> 20;
-            const int frac = z & ((1 << 20) - 1);
-            near_half |= (unsigned)(frac - (1 << 19) + 2) <= 4u;
+            const float kf = fmaf(bp[m], r100, kRoundMagic);           // low mantissa bits = rint(100*bp/S)
+            const float d = fmaf(bp[m], r100, kRoundMagic - kf);       // distance to that integer (kRoundMagic - kf is exact)
+            dmax = fmaxf(dmax, fabsf(d));
+            kb[m] = __float_as_uint(kf);
         }
-        if (near_half) {   // exact path (identical to belief_core): ~1e-5 of the records
+        float c0 = bp[0] * f0[0], c1 = bp[0] * f01[0];
 #pragma unroll
-            for (int m = 0; m < M; ++m) kq[m] = (uint32_t)__double2int_rn(__dmul_rn(ddiv_with(bp[m], S, rS), 100.0));
+        for (int m = 1; m < M; ++m) { c0 = fmaf(bp[m], f0[m], c0); c1 = fmaf(bp[m], f01[m], c1); }
+        const float uS = uf * S;
+        const uint32_t ap = uS < c0 ? 0u : (uS < c1 ? 1u : 2u);
+        const float gap = fminf(fabsf(uS - c0), fabsf(uS - c1));
+        exact = (dmax > kHalfWindow) | (gap < kCdfWindow * S) | (uf > 1.f - 2e-5f);
+        uint2 out;
+        out.x = __byte_perm(__byte_perm(kb[0], kb[1 < M ? 1 : 0], 0x0040u), __byte_perm(kb[2 < M ? 2 : 0], kb[3 < M ? 3 : 0], 0x0040u), 0x5410u);
+        if (M < 4) out.x &= (M == 2 ? 0xFFFFu : 0xFFFFFFu);
+        // byte 0 = k4 (M > 4), byte 1 = k5 (M > 5), byte 2 = predicted action, byte 3 = 0 (ap < 256: its byte 1 is zero)
+        out.y = M > 5 ? __byte_perm(__byte_perm(kb[M > 4 ? 4 : 0], kb[M > 5 ? 5 : 0], 0x0040u), ap, 0x5410u)
+                      : (M > 4 ? __byte_perm(kb[M > 4 ? 4 : 0], ap, 0x5450u) : ap << 16);
+        return out;
+    };
+    auto dump = [&](int64_t rec, uint2 out) {
+        if (belief_out) {
+#pragma unroll
+            for (int m = 0; m < M; ++m) belief_out[rec * M + m] = (uint8_t)(((m < 4 ? out.x : out.y) >> (8 * (m & 3))) & 0xFFu);
         }
-        uint32_t lo = 0, hi = 0;
+        if (pred_out) pred_out[rec] = (uint8_t)(out.y >> 16);
+    };
+
+    const int total = n_envs * KQ;
+    const int d_el = (int)blockDim.x / KQ, d_sq = (int)blockDim.x % KQ;
+    int el = (int)threadIdx.x / KQ, sq = (int)threadIdx.x % KQ;
+    uint8_t* const rec_base = P.records + ((e0 * N + i) * (int64_t)K) * IA2C_BELIEF_RECORD;   // record (e0, i, 0); block-local offsets fit 32 bits
+    const uint32_t env_stride = (uint32_t)N * (uint32_t)K * IA2C_BELIEF_RECORD;
+    const uint32_t d_off = (uint32_t)d_el * env_stride + (uint32_t)d_sq * (4 * IA2C_BELIEF_RECORD);
+    const uint32_t wrap_off = env_stride - (uint32_t)KQ * (4 * IA2C_BELIEF_RECORD);
+    uint32_t off = (uint32_t)el * env_stride + (uint32_t)sq * (4 * IA2C_BELIEF_RECORD);   // byte offset of the thread's quad
+    // Philox counter of the thread's quad: (global belief row) * KQ + sq, as a block-uniform 64-bit base plus a local part
+    const uint64_t ctr0 = (uint64_t)((P.env_offset + e0) * N + i) * (uint64_t)KQ;
+    const uint32_t row_ctr = (uint32_t)N * (uint32_t)KQ;                                     // one env further
+    uint32_t ctr = (uint32_t)el * row_ctr + (uint32_t)sq;
+    const uint32_t d_ctr = (uint32_t)d_el * row_ctr + (uint32_t)d_sq, wrap_ctr = row_ctr - (uint32_t)KQ;
+    const uint32_t c2 = (P.t & 0xFFFFu) | (kStreamBelief << 16);
+    auto quad_words = [&](uint32_t ctr_) -> uint4 {
+        const uint64_t index = ctr0 + ctr_;
+        return philox4x32_10_rk(make_uint4((uint32_t)index, (uint32_t)(index >> 32), c2, P.episode), P.rk);
+    };
+    // the four records of the NEXT iteration are fetched before the current quad is processed (software prefetch).  A quad
+    // that hangs over the end of the row (K not a multiple of 4) re-reads the row's last record and computes on it; only
+    // the stores and the count leave it out.
+    struct Quad { uint2 raw[4]; };
+    auto fetch = [&](uint32_t off_, int sq_, Quad& qd) {
+        const uint2* rp = reinterpret_cast<const uint2*>(rec_base + off_);
+        if (reset_prior) {
 #pragma unroll
-        for (int m = 0; m < M; ++m) {
-            if (m < 4) lo |= kq[m] << (8 * m); else hi |= kq[m] << (8 * (m - 4));
-            if (belief_out) belief_out[rec * M + m] = (uint8_t)kq[m];
+            for (int w = 0; w < 4; ++w) qd.raw[w] = make_uint2(0u, 0u);
+        } else if (4 * sq_ + 3 < K) {
+#pragma unroll
+            for (int w = 0; w < 4; ++w) qd.raw[w] = rp[w];
+        } else {
+#pragma unroll
+            for (int w = 0; w < 4; ++w) qd.raw[w] = rp[min(w, K - 1 - 4 * sq_)];
         }
-        // fp32 screening of the inverse-CDF decision
-        float pf[A];
-#pragma unroll
-        for (int a = 0; a < A; ++a) {
-            float acc = 0.f;
-#pragma unroll
-            for (int m = 0; m < M; ++m) acc = fmaf(bf[m], fa32[m * A + a], acc);
-            pf[a] = acc;
+    };
+    Quad cur;
+    if ((int)threadIdx.x < total) fetch(off, sq, cur);
+    for (int q = threadIdx.x; q < total; q += blockDim.x) {
+        int el_n = el + d_el, sq_n = sq + d_sq;
+        uint32_t off_n = off + d_off, ctr_n = ctr + d_ctr;
+        if (sq_n >= KQ) { sq_n -= KQ; ++el_n; off_n += wrap_off; ctr_n += wrap_ctr; }
+        Quad nxt = cur;
+        if (q + (int)blockDim.x < total) fetch(off_n, sq_n, nxt);
+        const int jj0 = 4 * sq;
+        const int n_valid = min(4, K - jj0);
+        const int64_t rec0 = ((e0 + el) * N + i) * (int64_t)K + jj0;   // only the optional dumps / injected tapes index with it
+        uint32_t words[4] = {0u, 0u, 0u, 0u};
+        if (!u_injected) {
+            const uint4 rnd = quad_words(ctr);
+            words[0] = rnd.x; words[1] = rnd.y; words[2] = rnd.z; words[3] = rnd.w;
         }
-        const float uf = (float)u;
-        float cf = pf[0];
-        int ap = 0;
-        bool found = uf < cf, risky = fabsf(uf - cf) < 1e-5f;
+        const uint32_t seen_w = seen4[q];
+        uint2 out[4];
+        uint32_t need = 0u;
 #pragma unroll
-        for (int a = 1; a < A; ++a) {
-            cf += pf[a];
-            risky |= fabsf(uf - cf) < 1e-5f;
-            if (!found && uf < cf) { ap = a; found = true; }
+        for (int w = 0; w < 4; ++w) {
+            float uf;
+            if (u_injected) uf = (float)u_injected[rec0 + min(w, n_valid - 1)];
+            else uf = __uint_as_float(0x3F800000u | (words[w] >> 9)) - 1.0f;   // floor(word / 2^9) * 2^-23: within 2^-23 of u
+            bool exact;
+            out[w] = screen_record(__byte_perm(seen_w, 0u, 0x4440u | (uint32_t)w), uf, cur.raw[w], exact);
+            need |= exact ? (1u << w) : 0u;
         }
-        if (risky) {   // exact sequence, identical to belief_core
-            double b[M];
+        need &= (1u << n_valid) - 1u;
+        if (need) {   // ~1 % of the quads: defer the flagged records to the exact pass below (their stored record stays untouched)
 #pragma unroll
-            for (int m = 0; m < M; ++m) b[m] = ddiv_with(bp[m], S, rS);
-            double c = 0.0;
-            ap = 0;
-            found = false;
-#pragma unroll
-            for (int a = 0; a < A; ++a) {
-                double acc = 0.0;
-#pragma unroll
-                for (int m = 0; m < M; ++m) acc = __dadd_rn(acc, __dmul_rn(b[m], fa[m * A + a]));
-                c = (a == 0) ? acc : __dadd_rn(c, acc);
-                if (!found && u < c) { ap = a; found = true; }
+            for (int w = 0; w < 4; ++w) {
+                if (need & (1u << w)) {
+                    const int pos = atomicAdd(&queue_n, 1);
+                    if (pos < kExactQueue) {
+                        queue[pos] = (uint16_t)(4 * q + w);
+                    } else {   // queue full (never seen in practice): the exact sequence right here
+                        const double u = u_injected ? u_injected[rec0 + w] : belief_word_to_unit_f64(words[w]);
+                        const uint32_t seen = (seen_w >> (8 * w)) & 0xFFu;
+                        out[w] = belief_exact_record<M>(bpt + seen * (M * 101), fa, cur.raw[w], prior_k, u);
+                        need &= ~(1u << w);
+                    }
+                }
             }
         }
-        hi |= (uint32_t)ap << 16;  // byte 6
-        *reinterpret_cast<uint2*>(P.records + rec * IA2C_BELIEF_RECORD) = make_uint2(lo, hi);
-        if (pred_out) pred_out[rec] = (uint8_t)ap;
-        if (FAST || P.pred_partner_out) atomicAdd(&counts[el * A + ap], 1);   // ptxas aggregates same-address lanes (REDUX)
-        return ap;
-    };
-    // the two records of the NEXT iteration are fetched before the current pair is processed (software prefetch: the
-    // kernel is bound by the latency of these loads at 4 blocks per SM).
-    struct Slot { int el, sl; int64_t rec; uint2 raw0, raw1; };
-    auto locate = [&](int q, Slot& s) {
-        s.el = (int)(((float)q + 0.5f) * inv_kp);   // q / KP (exact: q < 2^16, margin 0.5/KP)
-        s.sl = q - s.el * KP;
-        s.rec = ((e0 + s.el) * N + i) * (int64_t)K + 2 * s.sl;
-        s.raw0 = s.raw1 = make_uint2(0u, 0u);
-        if (!reset_prior) {
-            const uint2* rp = reinterpret_cast<const uint2*>(P.records + s.rec * IA2C_BELIEF_RECORD);
-            s.raw0 = rp[0];
-            if (2 * s.sl + 1 < K) s.raw1 = rp[1];
-        }
-    };
-    Slot cur;
-    if ((int)threadIdx.x < total) locate(threadIdx.x, cur);
-    for (int q = threadIdx.x; q < total; q += blockDim.x) {
-        Slot nxt = cur;
-        if (q + (int)blockDim.x < total) locate(q + blockDim.x, nxt);
-        const int el = cur.el, sl = cur.sl, jj = 2 * sl;
-        const bool two = jj + 1 < K;
-        const int64_t e = e0 + el, rec = cur.rec;
-        double u0, u1 = 0.0;
-        if (u_injected) {
-            u0 = u_injected[rec];
-            if (two) u1 = u_injected[rec + 1];
+        uint2* const wp = reinterpret_cast<uint2*>(rec_base + off);
+        uint32_t packed = 0u;
+        if (n_valid == 4 && !need) {
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+                wp[w] = out[w];
+                packed += 1u << (10u * (out[w].y >> 16));
+            }
         } else {
-            philox_belief_pair(P.seed, P.episode, P.t, (uint64_t)((P.env_offset + e) * N + i), K, sl, u0, u1);
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+                if (w < n_valid && !(need & (1u << w))) {
+                    wp[w] = out[w];
+                    packed += 1u << (10u * (out[w].y >> 16));
+                }
+            }
         }
-        one_record(rec, el, jj, u0, cur.raw0);
-        if (two) one_record(rec + 1, el, jj + 1, u1, cur.raw1);
+        if (belief_out || pred_out) {
+#pragma unroll
+            for (int w = 0; w < 4; ++w)
+                if (w < n_valid && !(need & (1u << w))) dump(rec0 + w, out[w]);
+        }
+        if (FAST || P.pred_partner_out) {   // one REDUX + one shared atomic per group of lanes that share the env
+            const unsigned peers = __match_any_sync(__activemask(), el);
+            const uint32_t sum = __reduce_add_sync(peers, packed);
+            if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&counts[el], sum);
+        }
         cur = nxt;
+        el = el_n;
+        sq = sq_n;
+        off = off_n;
+        ctr = ctr_n;
+    }
+    __syncthreads();
+    // exact pass: the deferred records, one per thread, with the reference's fp64 sequence (dense: no lane waits for another's rare case)
+    const int n_deferred = min(queue_n, kExactQueue);
+    for (int x = threadIdx.x; x < n_deferred; x += blockDim.x) {
+        const int code = queue[x], q = code >> 2, w = code & 3;
+        const int el_ = q / KQ, sq_ = q - el_ * KQ;
+        const int64_t rec = ((e0 + el_) * N + i) * (int64_t)K + 4 * sq_ + w;
+        uint2* rp = reinterpret_cast<uint2*>(P.records + rec * IA2C_BELIEF_RECORD);
+        const uint2 raw = reset_prior ? make_uint2(0u, 0u) : *rp;
+        double u;
+        if (u_injected) {
+            u = u_injected[rec];
+        } else {
+            const uint4 rnd = quad_words((uint32_t)el_ * row_ctr + (uint32_t)sq_);
+            u = belief_word_to_unit_f64(w == 0 ? rnd.x : (w == 1 ? rnd.y : (w == 2 ? rnd.z : rnd.w)));
+        }
+        const uint32_t seen = (seen4[q] >> (8 * w)) & 0xFFu;
+        const uint2 out = belief_exact_record<M>(bpt + seen * (M * 101), fa, raw, prior_k, u);
+        *rp = out;
+        dump(rec, out);
+        if (FAST || P.pred_partner_out) atomicAdd(&counts[el_], 1u << (10u * (out.y >> 16)));
     }
     if (P.pred_partner_out) {
         __syncthreads();
-        for (int el = threadIdx.x; el < n_envs; el += blockDim.x) {
-            const int* c = counts + el * A;
-            int best = 0;
-#pragma unroll
-            for (int a = 1; a < A; ++a) best = c[a] > c[best] ? a : best;   // ties -> lowest action
-            P.pred_partner_out[(e0 + el) * N + i] = (uint8_t)best;
+        for (int x = threadIdx.x; x < n_envs; x += blockDim.x) {
+            const uint32_t c = counts[x];
+            const int c0 = c & 1023, c1 = (c >> 10) & 1023, c2n = c >> 20;
+            int best = 0, bc = c0;
+            if (c1 > bc) { best = 1; bc = c1; }
+            if (c2n > bc) best = 2;                                  // ties -> lowest action
+            P.pred_partner_out[(e0 + x) * N + i] = (uint8_t)best;
         }
     }
 }
 
 template <int M>
 int launch_pairs_table(PairsArgs& P, cudaStream_t stream) {
-    P.envs_per_block = std::max(1, std::min(64, 16384 / P.K));   // amortise the table build (~15 % of the instructions at 4096)
+    P.envs_per_block = std::max(1, std::min(128, 32768 / P.K));   // amortise the table build and the staging of the others' actions
     const int64_t env_blocks = (P.E + P.envs_per_block - 1) / P.envs_per_block;
-    size_t smem = (104 + 3 * M * 101 + M * 3) * sizeof(double) + ((M * 3 + 3) & ~3) * sizeof(float) +
-                  (size_t)P.envs_per_block * 3 * sizeof(int) + (size_t)P.envs_per_block * P.N;
+    size_t smem = (104 + 3 * M * 101 + M * 3) * sizeof(double) + (((3 * M * 101 + 3) & ~3) + ((2 * M + 3) & ~3)) * sizeof(float) +
+                  (size_t)P.envs_per_block * sizeof(uint32_t) + kExactQueue * sizeof(uint16_t) +
+                  (size_t)P.envs_per_block * (((size_t)P.K + 3) & ~size_t(3));
     smem = (smem + 15) & ~size_t(15);
     dim3 grid((unsigned)env_blocks, P.N);
     const bool fast = !P.reset_prior && !P.u_injected && !P.belief_out && !P.pred_out && P.pred_partner_out;
@@ -501,7 +679,11 @@ extern "C" int ia2c_belief_update_pairs(uint8_t* records, const double* filter_a
     IA2C_REQUIRE(N >= 2 && N <= 1023, "ia2c_belief_update_pairs: N=%d outside 2..1023", N);
     IA2C_REQUIRE(M >= 2 && M <= IA2C_MAX_MODELS, "ia2c_belief_update_pairs: M=%d outside 2..%d", M, IA2C_MAX_MODELS);
     PairsArgs P{records, filter_action, actions, u_injected, pred_out, belief_out, pred_partner_out,
-                E, env_offset, N, N - 1, 0, 0, 0, reset_prior, seed, episode, t};
+                E, env_offset, N, N - 1, 0, 0, 0, reset_prior, seed, episode, t, {}};
+    for (int r = 0; r < 10; ++r) {
+        P.rk[2 * r] = (uint32_t)seed + (uint32_t)r * 0x9E3779B9u;
+        P.rk[2 * r + 1] = (uint32_t)(seed >> 32) + (uint32_t)r * 0xBB67AE85u;
+    }
     cudaStream_t s = as_stream(stream);
     switch (M) {
         case 2: return launch_pairs<2>(P, s);

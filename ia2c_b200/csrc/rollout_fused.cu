@@ -125,11 +125,12 @@ __global__ void __launch_bounds__(kBlock) rollout_fused_kernel(ia2c_episode_desc
                 for (int jj = 0; jj < K; ++jj) ub_s[t & 3][jj][lane] = tp.ub[jj];
             } else {
 #pragma unroll
-                for (int sl = 0; sl < (K + 1) / 2; ++sl) {
-                    double u0, u1;
-                    philox_belief_pair(d.seed, d.episode, (uint32_t)t, (uint64_t)((d.env_offset + e) * N + i), K, sl, u0, u1);
-                    ub_s[t & 3][2 * sl][lane] = u0;
-                    if (2 * sl + 1 < K) ub_s[t & 3][2 * sl + 1][lane] = u1;
+                for (int sl = 0; sl < (K + 3) / 4; ++sl) {
+                    const uint4 r = philox_belief_quad(d.seed, d.episode, (uint32_t)t, (uint64_t)((d.env_offset + e) * N + i), K, sl);
+                    ub_s[t & 3][4 * sl][lane] = belief_word_to_unit_f64(r.x);
+                    if (4 * sl + 1 < K) ub_s[t & 3][4 * sl + 1][lane] = belief_word_to_unit_f64(r.y);
+                    if (4 * sl + 2 < K) ub_s[t & 3][4 * sl + 2][lane] = belief_word_to_unit_f64(r.z);
+                    if (4 * sl + 3 < K) ub_s[t & 3][4 * sl + 3][lane] = belief_word_to_unit_f64(r.w);
                 }
             }
         }

@@ -36,10 +36,10 @@ def global_agent_index(env_offset: int, local_env, agent, n_agents: int):
 
 
 def belief_draw_index(env_offset: int, local_env, agent, slot, n_agents: int):
-    """Philox counter of the belief stream (csrc/common.cuh: philox_belief_pair; oracle/philox.py: belief_uniforms):
-    one Philox block serves TWO modelled-other slots.  For the belief row r = (global env) * N + agent with
-    K = N-1 modelled others, slots (2s, 2s+1) share the draw at index r * ceil(K/2) + s.
-    -> (draw index, word pair): pair 0 = words (x, y), pair 1 = words (z, w)."""
-    kp = n_agents // 2          # ceil((N-1)/2)
+    """Philox counter of the belief stream (csrc/common.cuh: philox_belief_quad; oracle/philox.py: belief_uniforms):
+    one Philox block serves FOUR modelled-other slots.  For the belief row r = (global env) * N + agent with
+    K = N-1 modelled others, slots 4s .. 4s+3 share the draw at index r * ceil(K/4) + s.
+    -> (draw index, word): the slot's uniform is (word + 0.5) * 2^-32."""
+    kq = (n_agents + 2) // 4          # ceil((N-1)/4)
     row = (env_offset + local_env) * n_agents + agent
-    return row * kp + slot // 2, slot % 2
+    return row * kq + slot // 4, slot % 4

@@ -67,11 +67,11 @@ def uniform_f64(seed, stream, episode, t, index):
 
 def belief_uniforms(seed, episode, t, rows, K):
     """The belief sampler's uniforms u[..., jj] for belief rows `rows` (= env * N + agent, any shape) and K modelled
-    others.  One Philox block serves two slots (common.cuh: philox_belief_pair): slots (2s, 2s+1) of row r share
-    the draw at index r * ceil(K/2) + s; words (x0, x1) -> slot 2s, (x2, x3) -> slot 2s+1."""
+    others.  One Philox block serves FOUR slots (common.cuh: philox_belief_quad): slots 4s .. 4s+3 of row r share the
+    draw at index r * ceil(K/4) + s, word w -> slot 4s + w, and a slot's uniform is the centred 32-bit value
+    (word + 0.5) * 2^-32 (exact in float64; common.cuh: belief_word_to_unit_f64)."""
     rows = np.asarray(rows, dtype=np.uint64)
-    kp = (K + 1) // 2
-    idx = rows[..., None] * np.uint64(kp) + np.arange(kp, dtype=np.uint64)
-    x0, x1, x2, x3 = draw(seed, STREAM_BELIEF, episode, t, idx)
-    u = np.stack([_unit_f64(x0, x1), _unit_f64(x2, x3)], axis=-1).reshape(rows.shape + (2 * kp,))
-    return u[..., :K]
+    kq = (K + 3) // 4
+    idx = rows[..., None] * np.uint64(kq) + np.arange(kq, dtype=np.uint64)
+    words = np.stack(draw(seed, STREAM_BELIEF, episode, t, idx), axis=-1).reshape(rows.shape + (4 * kq,))
+    return ((words.astype(np.float64) + 0.5) * 2.0 ** -32)[..., :K]

@@ -16,18 +16,18 @@ def test_shard_envs_and_tapes():
     parts = [shard_tape(tape, 1, r, 4) for r in range(4)]
     assert np.array_equal(np.concatenate(parts, axis=1), tape) and shard_tape(None, 1, 0, 2) is None
     # Philox counters are global: rank 1's first belief row continues where rank 0's last one ended, and the layout is
-    # the one the oracle's generator (which mirrors the kernels) uses: slots (2s, 2s+1) of row r share draw r*ceil(K/2)+s
-    for n_agents in (2, 3, 5, 64):
-        kp = n_agents // 2
+    # the one the oracle's generator (which mirrors the kernels) uses: slots 4s..4s+3 of row r share draw r*ceil(K/4)+s
+    for n_agents in (2, 3, 5, 6, 64):
+        kq = (n_agents + 2) // 4
         last = belief_draw_index(0, 3, n_agents - 1, n_agents - 2, n_agents)
         first = belief_draw_index(4, 0, 0, 0, n_agents)
-        assert first == (last[0] + 1, 0) and last[0] == (4 * n_agents - 1) * kp + (n_agents - 2) // 2
+        assert first == (last[0] + 1, 0) and last[0] == (4 * n_agents - 1) * kq + (n_agents - 2) // 4
     from oracle import philox as P
-    rows = np.array([[5 * 3 + 1]])                                  # env 5, agent 1 of N=3 (K=2: one draw, two word pairs)
-    u = P.belief_uniforms(9, 2, 7, rows, 2)
-    idx, pair = belief_draw_index(4, 1, 1, 1, 3)                    # rank offset 4 + local env 1 = global env 5, slot 1
+    rows = np.array([[5 * 7 + 1]])                                  # env 5, agent 1 of N=7 (K=6: two draws)
+    u = P.belief_uniforms(9, 2, 7, rows, 6)
+    idx, word = belief_draw_index(4, 1, 1, 5, 7)                    # rank offset 4 + local env 1 = global env 5, slot 5
     x = P.draw(9, P.STREAM_BELIEF, 2, 7, np.array([idx]))
-    assert pair == 1 and u[0, 0, 1] == P._unit_f64(x[2], x[3])[0]
+    assert word == 1 and u[0, 0, 5] == (float(x[1][0]) + 0.5) * 2.0 ** -32
 
 
 def _worker(rank, world, port, E, out):
