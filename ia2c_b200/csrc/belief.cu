@@ -146,6 +146,7 @@ struct PairsArgs {
     int N, K, envs_per_block, agents_per_block, chunks_per_env, reset_prior;
     uint64_t seed;
     uint32_t episode, t;
+    uint32_t stage_offset;         // byte offset of the cp.async staging ring in dynamic shared memory (table kernel)
     uint32_t rk[20];               // Philox round keys (k0_r, k1_r), r = 0..9 — derived from seed on the host so that the
                                    // rounds read them straight from the constant bank (table kernel)
 };
@@ -349,6 +350,7 @@ __global__ void __launch_bounds__(kThreads, 2) belief_pairs_table_kernel(const _
     uint32_t* counts = reinterpret_cast<uint32_t*>(fcum + ((2 * M + 3) & ~3));   // [EC] packed 3 x 10 bits
     uint16_t* queue = reinterpret_cast<uint16_t*>(counts + EC);      // [kExactQueue] deferred records: 4 * quad + slot
     uint32_t* seen4 = reinterpret_cast<uint32_t*>(queue + kExactQueue);   // [EC][KQ]: the OTHERS' actions, 4 slots per word
+    unsigned char* stage = smem_raw + P.stage_offset;               // [kStages][kThreads][32 B] cp.async ring (16-byte aligned)
     pdl_release();
     // the table depends only on the agent's models: it is built while the kernel that samples this step's actions
     // may still be running (programmatic dependent launch); pdl_wait() below orders the reads of its output
@@ -403,45 +405,64 @@ __global__ void __launch_bounds__(kThreads, 2) belief_pairs_table_kernel(const _
     for (int m = 0; m < M; ++m) { f0[m] = fcum[m]; f01[m] = fcum[M + m]; }
     const uint32_t bpt32_s = (uint32_t)__cvta_generic_to_shared(bpt32);   // explicit shared-window addresses for the lookups
 
-    // fp32 screen of one record -> the packed record {posterior hundredths, predicted action in byte 6}; `exact` is set
-    // when a rounding or the inverse-CDF decision is too close to call in fp32
-    auto screen_record = [&](uint32_t seen, float uf, uint2 raw, bool& exact) -> uint2 {
-        const uint32_t row = bpt32_s + seen * (M * 101 * 4);
-        float bp[M];
+    // fp32 screen of TWO records at once (packed f32x2 arithmetic: one issue slot per pair of FMAs) -> the packed records
+    // {posterior hundredths, predicted action in byte 6}; bit w of the result is set when record w's rounding or its
+    // inverse-CDF decision is too close to call in fp32
+    const float2 magic2 = make_float2(kRoundMagic, kRoundMagic), minus1 = make_float2(-1.f, -1.f);
+    auto screen_pair = [&](uint32_t seenA, uint32_t seenB, float ufA, float ufB, uint2 rawA, uint2 rawB, uint2& outA, uint2& outB) -> uint32_t {
+        const uint32_t rowA = bpt32_s + seenA * (M * 101 * 4), rowB = bpt32_s + seenB * (M * 101 * 4);
+        float2 bp[M];
 #pragma unroll
         for (int m = 0; m < M; ++m) {
-            const uint32_t k = reset_prior ? (uint32_t)prior_k : __byte_perm(m < 4 ? raw.x : raw.y, 0u, 0x4440u | (uint32_t)(m & 3));
-            bp[m] = lds_f32(row + 4u * k + (uint32_t)(m * 101 * 4));
+            const uint32_t sel = 0x4440u | (uint32_t)(m & 3);
+            const uint32_t kA = reset_prior ? (uint32_t)prior_k : __byte_perm(m < 4 ? rawA.x : rawA.y, 0u, sel);
+            const uint32_t kB = reset_prior ? (uint32_t)prior_k : __byte_perm(m < 4 ? rawB.x : rawB.y, 0u, sel);
+            bp[m] = make_float2(lds_f32(rowA + 4u * kA + (uint32_t)(m * 101 * 4)), lds_f32(rowB + 4u * kB + (uint32_t)(m * 101 * 4)));
         }
-        float S = bp[0];
+        float2 S = bp[0];
 #pragma unroll
-        for (int m = 1; m < M; ++m) S += bp[m];
-        float r;
-        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(S));
-        const float r100 = r * 100.f;
-        uint32_t kb[M];
-        float dmax = 0.f;
+        for (int m = 1; m < M; ++m) S = __fadd2_rn(S, bp[m]);
+        float rA, rB;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rA) : "f"(S.x));
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rB) : "f"(S.y));
+        const float2 r100 = __fmul2_rn(make_float2(rA, rB), make_float2(100.f, 100.f));
+        float2 kf[M];
+        float dmaxA = 0.f, dmaxB = 0.f;
 #pragma unroll
         for (int m = 0; m < M; ++m) {
-            const float kf = fmaf(bp[m], r100, kRoundMagic);           // low mantissa bits = rint(100*bp/S)
-            const float d = fmaf(bp[m], r100, kRoundMagic - kf);       // distance to that integer (kRoundMagic - kf is exact)
-            dmax = fmaxf(dmax, fabsf(d));
-            kb[m] = __float_as_uint(kf);
+            kf[m] = __ffma2_rn(bp[m], r100, magic2);                       // low mantissa bits = rint(100*bp/S)
+            const float2 nk = __ffma2_rn(kf[m], minus1, magic2);           // magic - kf, exact
+            const float2 d = __ffma2_rn(bp[m], r100, nk);                  // distance to that integer
+            dmaxA = fmaxf(dmaxA, fabsf(d.x));
+            dmaxB = fmaxf(dmaxB, fabsf(d.y));
         }
-        float c0 = bp[0] * f0[0], c1 = bp[0] * f01[0];
+        float2 c0 = __fmul2_rn(bp[0], make_float2(f0[0], f0[0])), c1 = __fmul2_rn(bp[0], make_float2(f01[0], f01[0]));
 #pragma unroll
-        for (int m = 1; m < M; ++m) { c0 = fmaf(bp[m], f0[m], c0); c1 = fmaf(bp[m], f01[m], c1); }
-        const float uS = uf * S;
-        const uint32_t ap = uS < c0 ? 0u : (uS < c1 ? 1u : 2u);
-        const float gap = fminf(fabsf(uS - c0), fabsf(uS - c1));
-        exact = (dmax > kHalfWindow) | (gap < kCdfWindow * S) | (uf > 1.f - 2e-5f);
-        uint2 out;
-        out.x = __byte_perm(__byte_perm(kb[0], kb[1 < M ? 1 : 0], 0x0040u), __byte_perm(kb[2 < M ? 2 : 0], kb[3 < M ? 3 : 0], 0x0040u), 0x5410u);
-        if (M < 4) out.x &= (M == 2 ? 0xFFFFu : 0xFFFFFFu);
-        // byte 0 = k4 (M > 4), byte 1 = k5 (M > 5), byte 2 = predicted action, byte 3 = 0 (ap < 256: its byte 1 is zero)
-        out.y = M > 5 ? __byte_perm(__byte_perm(kb[M > 4 ? 4 : 0], kb[M > 5 ? 5 : 0], 0x0040u), ap, 0x5410u)
-                      : (M > 4 ? __byte_perm(kb[M > 4 ? 4 : 0], ap, 0x5450u) : ap << 16);
-        return out;
+        for (int m = 1; m < M; ++m) {
+            c0 = __ffma2_rn(bp[m], make_float2(f0[m], f0[m]), c0);
+            c1 = __ffma2_rn(bp[m], make_float2(f01[m], f01[m]), c1);
+        }
+        const float2 uS = __fmul2_rn(make_float2(ufA, ufB), S);
+        const float2 win = __fmul2_rn(S, make_float2(kCdfWindow, kCdfWindow));
+        const float2 g0 = __ffma2_rn(c0, minus1, uS), g1 = __ffma2_rn(c1, minus1, uS);   // uS - c0, uS - c1
+        const uint32_t apA = uS.x < c0.x ? 0u : (uS.x < c1.x ? 1u : 2u), apB = uS.y < c0.y ? 0u : (uS.y < c1.y ? 1u : 2u);
+        const bool exA = (dmaxA > kHalfWindow) | (fminf(fabsf(g0.x), fabsf(g1.x)) < win.x) | (ufA > 1.f - 2e-5f);
+        const bool exB = (dmaxB > kHalfWindow) | (fminf(fabsf(g0.y), fabsf(g1.y)) < win.y) | (ufB > 1.f - 2e-5f);
+        auto pack = [&](bool second, uint32_t ap) -> uint2 {
+            uint32_t kb[M];
+#pragma unroll
+            for (int m = 0; m < M; ++m) kb[m] = __float_as_uint(second ? kf[m].y : kf[m].x);
+            uint2 out;
+            out.x = __byte_perm(__byte_perm(kb[0], kb[1 < M ? 1 : 0], 0x0040u), __byte_perm(kb[2 < M ? 2 : 0], kb[3 < M ? 3 : 0], 0x0040u), 0x5410u);
+            if (M < 4) out.x &= (M == 2 ? 0xFFFFu : 0xFFFFFFu);
+            // byte 0 = k4 (M > 4), byte 1 = k5 (M > 5), byte 2 = predicted action, byte 3 = 0 (ap < 256: its byte 1 is zero)
+            out.y = M > 5 ? __byte_perm(__byte_perm(kb[M > 4 ? 4 : 0], kb[M > 5 ? 5 : 0], 0x0040u), ap, 0x5410u)
+                          : (M > 4 ? __byte_perm(kb[M > 4 ? 4 : 0], ap, 0x5450u) : ap << 16);
+            return out;
+        };
+        outA = pack(false, apA);
+        outB = pack(true, apB);
+        return (exA ? 1u : 0u) | (exB ? 2u : 0u);
     };
     auto dump = [&](int64_t rec, uint2 out) {
         if (belief_out) {
@@ -469,31 +490,55 @@ __global__ void __launch_bounds__(kThreads, 2) belief_pairs_table_kernel(const _
         const uint64_t index = ctr0 + ctr_;
         return philox4x32_10_rk(make_uint4((uint32_t)index, (uint32_t)(index >> 32), c2, P.episode), P.rk);
     };
-    // the four records of the NEXT iteration are fetched before the current quad is processed (software prefetch).  A quad
-    // that hangs over the end of the row (K not a multiple of 4) re-reads the row's last record and computes on it; only
-    // the stores and the count leave it out.
-    struct Quad { uint2 raw[4]; };
-    auto fetch = [&](uint32_t off_, int sq_, Quad& qd) {
-        const uint2* rp = reinterpret_cast<const uint2*>(rec_base + off_);
-        if (reset_prior) {
+    // The record stream is staged through shared memory with cp.async: every thread owns one 32-byte slot per stage and
+    // copies its quad of iteration it + kStages - 1 while it computes on iteration it — kStages - 1 quads (up to 96 B) per
+    // thread in flight without holding a register, and no barrier (a thread only reads what it copied itself).  A quad that
+    // hangs over the end of the row (K not a multiple of 4) re-reads the row's last record and computes on it; only the
+    // stores and the count leave it out.
+    constexpr int kStages = 4;
+    const uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(stage) + threadIdx.x * 32u;
+    auto issue = [&](uint32_t off_, int sq_, int slot, bool live) {
+        if (live && !reset_prior) {
+            const uint8_t* rp = rec_base + off_;
+            const uint32_t dst = stage_s + (uint32_t)slot * (kThreads * 32u);
+            const int last = K - 1 - 4 * sq_;                               // >= 3 for a whole quad
 #pragma unroll
-            for (int w = 0; w < 4; ++w) qd.raw[w] = make_uint2(0u, 0u);
-        } else if (4 * sq_ + 3 < K) {
-#pragma unroll
-            for (int w = 0; w < 4; ++w) qd.raw[w] = rp[w];
-        } else {
-#pragma unroll
-            for (int w = 0; w < 4; ++w) qd.raw[w] = rp[min(w, K - 1 - 4 * sq_)];
+            for (int w = 0; w < 4; ++w)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 8u * w), "l"(rp + 8 * min(w, last)) : "memory");
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    Quad cur;
-    if ((int)threadIdx.x < total) fetch(off, sq, cur);
+    // (el, sq, off, ctr) of the quad the thread will ISSUE next; the quad it COMPUTES on trails kStages - 1 iterations behind
+    int el_i = el, sq_i = sq;
+    uint32_t off_i = off;
+    auto advance = [&](int& el_, int& sq_, uint32_t& off_, uint32_t* ctr_) {
+        el_ += d_el; sq_ += d_sq; off_ += d_off;
+        if (ctr_) *ctr_ += d_ctr;
+        if (sq_ >= KQ) { sq_ -= KQ; ++el_; off_ += wrap_off; if (ctr_) *ctr_ += wrap_ctr; }
+    };
+    int q_i = threadIdx.x;
+#pragma unroll
+    for (int st = 0; st < kStages - 1; ++st) {
+        issue(off_i, sq_i, st, q_i < total);
+        advance(el_i, sq_i, off_i, nullptr);
+        q_i += blockDim.x;
+    }
+    int slot = 0;
     for (int q = threadIdx.x; q < total; q += blockDim.x) {
-        int el_n = el + d_el, sq_n = sq + d_sq;
-        uint32_t off_n = off + d_off, ctr_n = ctr + d_ctr;
-        if (sq_n >= KQ) { sq_n -= KQ; ++el_n; off_n += wrap_off; ctr_n += wrap_ctr; }
-        Quad nxt = cur;
-        if (q + (int)blockDim.x < total) fetch(off_n, sq_n, nxt);
+        issue(off_i, sq_i, (slot + kStages - 1) % kStages, q_i < total);
+        advance(el_i, sq_i, off_i, nullptr);
+        q_i += blockDim.x;
+        asm volatile("cp.async.wait_group %0;" ::"n"(kStages - 1) : "memory");
+        uint2 raw[4];
+        {
+            const uint32_t src = stage_s + (uint32_t)slot * (kThreads * 32u);
+            uint4 a, b;
+            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "r"(src) : "memory");
+            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "r"(src + 16u) : "memory");
+            raw[0] = make_uint2(a.x, a.y); raw[1] = make_uint2(a.z, a.w); raw[2] = make_uint2(b.x, b.y); raw[3] = make_uint2(b.z, b.w);
+            if (reset_prior) raw[0] = raw[1] = raw[2] = raw[3] = make_uint2(0u, 0u);
+        }
+        slot = (slot + 1) % kStages;
         const int jj0 = 4 * sq;
         const int n_valid = min(4, K - jj0);
         const int64_t rec0 = ((e0 + el) * N + i) * (int64_t)K + jj0;   // only the optional dumps / injected tapes index with it
@@ -504,16 +549,14 @@ __global__ void __launch_bounds__(kThreads, 2) belief_pairs_table_kernel(const _
         }
         const uint32_t seen_w = seen4[q];
         uint2 out[4];
-        uint32_t need = 0u;
+        float uf[4];
 #pragma unroll
         for (int w = 0; w < 4; ++w) {
-            float uf;
-            if (u_injected) uf = (float)u_injected[rec0 + min(w, n_valid - 1)];
-            else uf = __uint_as_float(0x3F800000u | (words[w] >> 9)) - 1.0f;   // floor(word / 2^9) * 2^-23: within 2^-23 of u
-            bool exact;
-            out[w] = screen_record(__byte_perm(seen_w, 0u, 0x4440u | (uint32_t)w), uf, cur.raw[w], exact);
-            need |= exact ? (1u << w) : 0u;
+            if (u_injected) uf[w] = (float)u_injected[rec0 + min(w, n_valid - 1)];
+            else uf[w] = __uint_as_float(0x3F800000u | (words[w] >> 9)) - 1.0f;   // floor(word / 2^9) * 2^-23: within 2^-23 of u
         }
+        uint32_t need = screen_pair(__byte_perm(seen_w, 0u, 0x4440u), __byte_perm(seen_w, 0u, 0x4441u), uf[0], uf[1], raw[0], raw[1], out[0], out[1]);
+        need |= screen_pair(__byte_perm(seen_w, 0u, 0x4442u), __byte_perm(seen_w, 0u, 0x4443u), uf[2], uf[3], raw[2], raw[3], out[2], out[3]) << 2;
         need &= (1u << n_valid) - 1u;
         if (need) {   // ~1 % of the quads: defer the flagged records to the exact pass below (their stored record stays untouched)
 #pragma unroll
@@ -525,7 +568,7 @@ __global__ void __launch_bounds__(kThreads, 2) belief_pairs_table_kernel(const _
                     } else {   // queue full (never seen in practice): the exact sequence right here
                         const double u = u_injected ? u_injected[rec0 + w] : belief_word_to_unit_f64(words[w]);
                         const uint32_t seen = (seen_w >> (8 * w)) & 0xFFu;
-                        out[w] = belief_exact_record<M>(bpt + seen * (M * 101), fa, cur.raw[w], prior_k, u);
+                        out[w] = belief_exact_record<M>(bpt + seen * (M * 101), fa, raw[w], prior_k, u);
                         need &= ~(1u << w);
                     }
                 }
@@ -558,12 +601,9 @@ __global__ void __launch_bounds__(kThreads, 2) belief_pairs_table_kernel(const _
             const uint32_t sum = __reduce_add_sync(peers, packed);
             if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&counts[el], sum);
         }
-        cur = nxt;
-        el = el_n;
-        sq = sq_n;
-        off = off_n;
-        ctr = ctr_n;
+        advance(el, sq, off, &ctr);
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
     // exact pass: the deferred records, one per thread, with the reference's fp64 sequence (dense: no lane waits for another's rare case)
     const int n_deferred = min(queue_n, kExactQueue);
@@ -607,6 +647,8 @@ int launch_pairs_table(PairsArgs& P, cudaStream_t stream) {
                   (size_t)P.envs_per_block * sizeof(uint32_t) + kExactQueue * sizeof(uint16_t) +
                   (size_t)P.envs_per_block * (((size_t)P.K + 3) & ~size_t(3));
     smem = (smem + 15) & ~size_t(15);
+    P.stage_offset = (uint32_t)smem;
+    smem += (size_t)4 * kThreads * 32;   // kStages slots of 32 B per thread
     dim3 grid((unsigned)env_blocks, P.N);
     const bool fast = !P.reset_prior && !P.u_injected && !P.belief_out && !P.pred_out && P.pred_partner_out;
     if (fast) {
@@ -679,7 +721,7 @@ extern "C" int ia2c_belief_update_pairs(uint8_t* records, const double* filter_a
     IA2C_REQUIRE(N >= 2 && N <= 1023, "ia2c_belief_update_pairs: N=%d outside 2..1023", N);
     IA2C_REQUIRE(M >= 2 && M <= IA2C_MAX_MODELS, "ia2c_belief_update_pairs: M=%d outside 2..%d", M, IA2C_MAX_MODELS);
     PairsArgs P{records, filter_action, actions, u_injected, pred_out, belief_out, pred_partner_out,
-                E, env_offset, N, N - 1, 0, 0, 0, reset_prior, seed, episode, t, {}};
+                E, env_offset, N, N - 1, 0, 0, 0, reset_prior, seed, episode, t, 0u, {}};
     for (int r = 0; r < 10; ++r) {
         P.rk[2 * r] = (uint32_t)seed + (uint32_t)r * 0x9E3779B9u;
         P.rk[2 * r + 1] = (uint32_t)(seed >> 32) + (uint32_t)r * 0xBB67AE85u;
