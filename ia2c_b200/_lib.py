@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libia2c_b200.so")
+LIB_PATH = os.environ.get("IA2C_B200_LIB") or os.path.join(_PKG, "libia2c_b200.so")   # override: A/B runs of alternative builds
 
 vp = C.c_void_p
 i32, i64, u32, u64, f32, f64 = C.c_int32, C.c_int64, C.c_uint32, C.c_uint64, C.c_float, C.c_double

@@ -490,13 +490,13 @@ __global__ void __launch_bounds__(kThreads, 2) belief_pairs_table_kernel(const _
         const uint64_t index = ctr0 + ctr_;
         return philox4x32_10_rk(make_uint4((uint32_t)index, (uint32_t)(index >> 32), c2, P.episode), P.rk);
     };
-    // The record stream is staged through shared memory with cp.async: every thread owns one 32-byte slot per stage and
-    // copies its quad of iteration it + kStages - 1 while it computes on iteration it — kStages - 1 quads (up to 96 B) per
+    // The record stream is staged through shared memory with cp.async: every thread owns four 8-byte slots per stage
+    // (laid out [slot][thread]: conflict-free) and copies its quad of iteration it + kStages - 1 while it computes on iteration it — kStages - 1 quads (up to 96 B) per
     // thread in flight without holding a register, and no barrier (a thread only reads what it copied itself).  A quad that
     // hangs over the end of the row (K not a multiple of 4) re-reads the row's last record and computes on it; only the
     // stores and the count leave it out.
     constexpr int kStages = 4;
-    const uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(stage) + threadIdx.x * 32u;
+    const uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(stage) + threadIdx.x * 8u;   // [stage][slot w][thread]: conflict-free
     auto issue = [&](uint32_t off_, int sq_, int slot, bool live) {
         if (live && !reset_prior) {
             const uint8_t* rp = rec_base + off_;
@@ -504,7 +504,7 @@ __global__ void __launch_bounds__(kThreads, 2) belief_pairs_table_kernel(const _
             const int last = K - 1 - 4 * sq_;                               // >= 3 for a whole quad
 #pragma unroll
             for (int w = 0; w < 4; ++w)
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 8u * w), "l"(rp + 8 * min(w, last)) : "memory");
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + (kThreads * 8u) * w), "l"(rp + 8 * min(w, last)) : "memory");
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
@@ -532,10 +532,9 @@ __global__ void __launch_bounds__(kThreads, 2) belief_pairs_table_kernel(const _
         uint2 raw[4];
         {
             const uint32_t src = stage_s + (uint32_t)slot * (kThreads * 32u);
-            uint4 a, b;
-            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "r"(src) : "memory");
-            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "r"(src + 16u) : "memory");
-            raw[0] = make_uint2(a.x, a.y); raw[1] = make_uint2(a.z, a.w); raw[2] = make_uint2(b.x, b.y); raw[3] = make_uint2(b.z, b.w);
+#pragma unroll
+            for (int w = 0; w < 4; ++w)
+                asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(raw[w].x), "=r"(raw[w].y) : "r"(src + (kThreads * 8u) * w) : "memory");
             if (reset_prior) raw[0] = raw[1] = raw[2] = raw[3] = make_uint2(0u, 0u);
         }
         slot = (slot + 1) % kStages;
