@@ -80,6 +80,8 @@ SIGNATURES = {
     "ia2c_actor_loss": (C.c_int, [vp, vp, vp, f32, vp, vp, vp, vp, vp, i64, i32, vp]),
     "ia2c_loss_workspace": (C.c_size_t, [i64]),
     "ia2c_adam_step": (C.c_int, [vp, vp, vp, vp, vp, vp, f64, f64, f64, f64, i32, i32, vp]),
+    "ia2c_net_update_workspace": (C.c_size_t, [i64, i32, i32]),
+    "ia2c_net_update": (C.c_int, [i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_float, f64, vp, vp, vp, i64, i32, i32, vp]),
     "ia2c_episode_partials_floats": (C.c_size_t, [_DP]),
     "ia2c_rollout_fused_supported": (C.c_int, [i32, i32]),
     "ia2c_rollout": (C.c_int, [_DP, vp]),

@@ -286,6 +286,61 @@ def _index_like(act, lead_shape, who):
     return idx
 
 
+def _no_graph(t):
+    return not (isinstance(t, torch.Tensor) and t.requires_grad)
+
+
+def _fused_update(net, optimizer, kind, obs, act, signal, beta, who):
+    """batch_update without a framework graph (target / advantage carries none): ONE C call, ``ia2c_net_update`` —
+    forward, loss, backward, Adam — on a cached workspace.  Same arithmetic as the autograd path (the same kernels, or
+    for wide dense inputs the single-pass kernel that reads the observations once).  Shares the optimizer's state, so
+    fused and autograd updates can alternate.  -> (loss tensor, status tensor or None), or None if not applicable."""
+    group = optimizer.param_groups[0]
+    if len(optimizer.param_groups) != 1 or tuple(group["betas"]) != (0.9, 0.999) or group["eps"] != 1e-8:
+        return None
+    lib = _lib.load()
+    p = net.flat
+    dev = p.device
+    F_, O = net.state_dim, net.action_dim
+    if _is_index_input(obs):
+        idx, flat_idx = _checked_indices(obs, F_, dev)
+        lead, x2, rows = tuple(idx.shape), None, flat_idx.numel()
+    else:
+        x = obs if (isinstance(obs, torch.Tensor) and obs.device == dev) else torch.as_tensor(obs).to(dev)
+        if x.shape[-1] != F_:
+            return None
+        lead, flat_idx = tuple(x.shape[:-1]), None
+        x2 = x.detach().reshape(-1, F_).to(torch.float32).contiguous()
+        rows = x2.shape[0]
+    a = _index_like(torch.as_tensor(act), lead, who).to(dev).reshape(-1).to(torch.int32).contiguous()
+    sig = torch.as_tensor(signal).detach().to(dev, torch.float32).reshape(-1).contiguous()
+    if rows == 0 or a.numel() != rows or sig.numel() != rows:
+        return None
+    st = optimizer.state[p]
+    if not st:
+        st["exp_avg"] = torch.zeros_like(p).reshape(-1)
+        st["exp_avg_sq"] = torch.zeros_like(p).reshape(-1)
+        st["step"] = torch.zeros(1, dtype=torch.int32, device=dev)
+    if p.grad is None:
+        p.grad = torch.zeros_like(p)          # the actor's running gradient sum starts at zero (Q2); the critic's is overwritten
+    cache = net.__dict__.setdefault("_fused_cache", {})
+    key = (rows, F_, O)
+    if key not in cache:
+        cache.clear()
+        n = int(lib.ia2c_net_update_workspace(rows, F_, O))
+        cache[key] = (torch.empty(n, dtype=torch.float32, device=dev), torch.empty((), dtype=torch.float32, device=dev),
+                      torch.zeros(1, dtype=torch.int32, device=dev))
+    ws, loss, status = cache[key]
+    if kind == 1:
+        status.zero_()
+    with torch.no_grad():
+        _lib.check(lib.ia2c_net_update(kind, _lib.ptr(p.data.view(-1)), _lib.ptr(p.grad.view(-1)), _lib.ptr(st["exp_avg"]),
+                                       _lib.ptr(st["exp_avg_sq"]), _lib.ptr(st["step"]), _lib.ptr(x2), _lib.ptr(flat_idx), _lib.ptr(a),
+                                       _lib.ptr(sig), float(beta), float(group["lr"]), _lib.ptr(loss), _lib.ptr(status), _lib.ptr(ws),
+                                       rows, F_, O, _lib.stream_ptr()), "ia2c_net_update")
+    return loss, (status if kind == 1 else None)
+
+
 class CriticNetwork:
     def __init__(self, name, n_features, critic_actions, lr, cuda=False):
         self.name = name
@@ -307,6 +362,14 @@ class CriticNetwork:
 
     def batch_update(self, obs, act, target, action_distribution=False):
         dev = self.net.flat.device
+        if not action_distribution and _no_graph(target) and _no_graph(obs):   # no graph to feed: one fused C call
+            fused = _fused_update(self.net, self.optimizer, 0, obs, act, target, 0.0, "CriticNetwork.batch_update")
+            if fused is not None:
+                self.losses.append(fused[0].cpu().numpy())
+                if len(self.losses) > 20:
+                    del self.losses[0]
+                self.critic_loss = np.mean(self.losses)
+                return
         self.optimizer.zero_grad()
         Q = self.net.forward(obs)
         target_d = target.to(dev)  # differentiable copy: gradient flows back into the caller's graph (Q8)
@@ -384,6 +447,20 @@ class ActorNetwork:
 
     def batch_update(self, obs, act, adv, retain=False):
         dev = self.net.flat.device
+        if _no_graph(adv) and _no_graph(obs):   # gradient-free advantage (ia2c.py:127): one fused C call
+            adv_f = adv
+            if isinstance(adv, torch.Tensor) and adv.dim() >= 2 and adv.shape[-1] == 1:
+                adv_f = adv.squeeze(-1)
+            fused = _fused_update(self.net, self.optimizer, 1, obs, act, adv_f, self.beta, "ActorNetwork.batch_update")
+            if fused is not None:
+                vals = torch.stack([fused[0], fused[1][0].to(torch.float32)]).cpu().numpy()   # loss + status: one copy, one sync
+                if int(vals[1]):  # the reference's Categorical validation raises here
+                    raise ValueError("Expected parameter probs of distribution Categorical to satisfy the constraint Simplex()")
+                self.losses.append(vals[0])
+                if len(self.losses) > 20:
+                    del self.losses[0]
+                self.actor_loss = np.mean(self.losses)
+                return
         probs = self.net.forward(obs)
         idx = _index_like(torch.as_tensor(act), probs.shape[:-1], "ActorNetwork.batch_update").to(dev)
         adv_d = adv.to(dev)  # differentiable copy (the advantage may carry gradient, Q7)

@@ -177,6 +177,23 @@ int ia2c_adam_step(float* params, const float* grad, float* grad_accum, float* e
                    int32_t* step_count, double lr, double beta1, double beta2, double eps,
                    int32_t nets, int32_t P, void* stream);
 
+/* CriticNetwork.batch_update (kind 0; ac_nets.py:62-72) / ActorNetwork.batch_update (kind 1; ac_nets.py:112-119) in ONE
+ * call for a target / advantage that carries no autograd graph: forward, loss (ia2c_critic_loss / ia2c_actor_loss
+ * semantics), backward, Adam step (torch defaults: betas 0.9 / 0.999, eps 1e-8).
+ *   params / exp_avg / exp_avg_sq float[P], step_count int32[1] (device, incremented): as ia2c_adam_step;
+ *   grad float[P]: kind 0 -> overwritten with this update's gradient (the critic calls zero_grad first);
+ *                  kind 1 -> grad += gradient, and Adam steps on the running sum (the actor never zeroes it, Q2);
+ *   exactly one of x float[rows,F] (dense rows) and idx int64[rows] (class indices standing for one_hot rows);
+ *   act int32[rows]; signal float[rows] = target (kind 0) or advantage (kind 1); beta = entropy weight (kind 1);
+ *   loss_out float[1] (device); status_out int32[1] (kind 1; set to 1 if a probability row is not a simplex);
+ *   workspace float[ia2c_net_update_workspace(rows,F,O)].
+ * Wide dense inputs (the a2c_test.py shape) take a single-pass kernel that reads x ONCE (bulk async copies into shared
+ * memory, both the layer-1 products and the layer-1 weight gradient computed from the staged tile). */
+size_t ia2c_net_update_workspace(int64_t rows, int32_t F, int32_t O);
+int ia2c_net_update(int32_t kind, float* params, float* grad, float* exp_avg, float* exp_avg_sq, int32_t* step_count,
+                    const float* x, const int64_t* idx, const int32_t* act, const float* signal, float beta, double lr,
+                    float* loss_out, int32_t* status_out, float* workspace, int64_t rows, int32_t F, int32_t O, void* stream);
+
 /* ------------------------------------------------------------------ fused IA2C trainer -------- */
 /* One descriptor for the whole episode of ia2c.py:62-129, generalised to N agents (DESIGN.md "Org-N").
  * Trajectory layout in HBM (time-major, env-minor, structure of arrays):

@@ -246,3 +246,45 @@ def test_index_input_rejects_out_of_range_classes():
     c = CriticNetwork("c", 500, 6, 1e-3)
     with pytest.raises(RuntimeError, match="Class values"):
         c.run_main(torch.tensor([[3, 500]]))
+
+
+@pytest.mark.parametrize("kind,rows,F,O", [(0, 5000, 500, 6), (1, 5000, 500, 6), (0, 1024 + 17, 64, 8), (1, 2048, 128, 3), (1, 4100, 500, 6)])
+def test_single_pass_update_equals_the_kernel_sequence(kind, rows, F, O):
+    """ia2c_net_update: the single-pass kernel for wide dense rows (bulk async copies, X read once) against the forward / loss /
+    backward / Adam kernel sequence behind the same entry point (IA2C_NO_SINGLE_PASS), which the golden tapes pin."""
+    import os
+    import torch
+    from ia2c_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.RandomState(rows + F + O + kind)
+    P = NN.n_params(F, O)
+    flat0 = (rng.randn(P) * 0.3).astype(np.float32)
+    x = np.zeros((rows, F), dtype=np.float32)
+    x[np.arange(rows), rng.randint(0, F, size=rows)] = 1.0          # one-hot rows (a2c_test.py:57) ...
+    x[: rows // 2] += (rng.rand(rows // 2, F) < 0.05) * rng.randn(rows // 2, F).astype(np.float32)   # ... and some dense ones
+    act = rng.randint(0, O, size=rows).astype(np.int32)
+    sig = rng.randn(rows).astype(np.float32)
+    grad0 = (rng.randn(P) * 0.01).astype(np.float32)               # the actor's running gradient sum is not zero
+    out = {}
+    for mode in ("sequence", "single"):
+        if mode == "sequence":
+            os.environ["IA2C_NO_SINGLE_PASS"] = "1"
+        else:
+            os.environ.pop("IA2C_NO_SINGLE_PASS", None)
+        p, g = dev(flat0.copy()), dev(grad0.copy())
+        m, v = dev(np.zeros(P, np.float32)), dev(np.zeros(P, np.float32))
+        step = torch.zeros(1, dtype=torch.int32, device="cuda")
+        loss, status = torch.zeros(1, device="cuda"), torch.zeros(1, dtype=torch.int32, device="cuda")
+        ws = torch.empty(int(lib.ia2c_net_update_workspace(rows, F, O)), dtype=torch.float32, device="cuda")
+        xd, ad, sd = dev(x), dev(act), dev(sig)
+        for it in range(2):
+            P_ = lambda t: t.data_ptr()
+            _lib.check(lib.ia2c_net_update(kind, P_(p), P_(g), P_(m), P_(v), P_(step), P_(xd), None, P_(ad), P_(sd), 0.01,
+                                           5e-4, P_(loss), P_(status), P_(ws), rows, F, O, None))
+        torch.cuda.synchronize()
+        out[mode] = (host(p), host(g), float(loss.item()), int(step.item()), int(status.item()))
+    os.environ.pop("IA2C_NO_SINGLE_PASS", None)
+    (p1, g1, l1, s1, st1), (p2, g2, l2, s2, st2) = out["sequence"], out["single"]
+    assert s1 == s2 == 2 and st1 == st2 == 0
+    assert rel_err(l2, l1) < RTOL and rel_err(g2, g1) < RTOL and rel_err(p2, p1) < RTOL
+    assert not np.array_equal(p1, flat0)
