@@ -96,9 +96,10 @@ __global__ void __launch_bounds__(kUThreads, 1) net_update_dense_kernel(const __
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem);            // [kUStages]
     float* xs = reinterpret_cast<float*>(smem + 128);              // [kUStages][kURows][F]
     float* wsm = xs + (size_t)kUStages * kURows * F;               // [n_small] small parameters
-    float* rec = wsm + ((n_small + 3) & ~3);                       // [kURows][kRec]
+    float* rec0 = wsm + ((n_small + 3) & ~3);                      // [2][kURows][kRec]: row records, double-buffered
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int c = lane & 7, grp = lane & ~7;                       // tail: 8 lanes per row, c = inner index
+    pdl_release();                                                 // the reduce + Adam kernel may be scheduled; it waits for this grid
     if (tid == 0) {
         for (int s = 0; s < kUStages; ++s) mbar_init(smem_u32(bars + s), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -170,6 +171,7 @@ __global__ void __launch_bounds__(kUThreads, 1) net_update_dense_kernel(const __
         const uint32_t parity = (uint32_t)(use / kUStages) & 1u;
         const int nr = tile_rows(tile);
         const float* xt = xs + (size_t)stage * kURows * F;
+        float* rec = rec0 + (use & 1) * (kURows * kRec);
         mbar_wait(smem_u32(bars + stage), parity);
         // ---------------- phase 1: z1 partial sums of the warp's four rows over the lane's features
         float2 acc[4][3];
@@ -271,7 +273,11 @@ __global__ void __launch_bounds__(kUThreads, 1) net_update_dense_kernel(const __
             if (c == 6) rr[26] = 1.f;
             if (c == 7) rr[27] = loss_row;
         }
-        __syncthreads();
+        __syncthreads();   // the ONLY block barrier per tile: records visible; every thread has finished phase 2 of the previous tile
+        if (tid == 0 && use > 0) {
+            const int next = tile + (kUStages - 1) * gridDim.x;       // goes into the stage of the previous tile
+            if (next < A.n_tiles) load_tile(next, (use - 1) % kUStages);
+        }
         // ---------------- phase 2: rank-1 updates of dW1 from the staged tile (thread = feature column) + the small sums
 #pragma unroll 4
         for (int r = 0; r < nr; ++r) {
@@ -286,13 +292,14 @@ __global__ void __launch_bounds__(kUThreads, 1) net_update_dense_kernel(const __
             gacc[1][0] = __ffma2_rn(make_float2(d03.x, d03.y), make_float2(xb, xb), gacc[1][0]);
             gacc[1][1] = __ffma2_rn(make_float2(d03.z, d03.w), make_float2(xb, xb), gacc[1][1]);
             gacc[1][2] = __ffma2_rn(d45, make_float2(xb, xb), gacc[1][2]);
-            sacc0 = fmaf(rr[ea0], rr[eb0], sacc0);
-            sacc1 = fmaf(rr[ea1], rr[eb1], sacc1);
         }
-        __syncthreads();                                    // every thread is done with this stage and with rec
-        if (tid == 0) {
-            const int next = tile + kUStages * gridDim.x;
-            if (next < A.n_tiles) load_tile(next, stage);
+        if (warp <= n_small / 32) {   // warp-uniform: the warps that own small sums (n_small + 1 <= 2 * 256 entries)
+#pragma unroll 4
+            for (int r = 0; r < nr; ++r) {
+                const float* rr = rec + r * kRec;
+                sacc0 = fmaf(rr[ea0], rr[eb0], sacc0);
+                if (n_small >= kUThreads) sacc1 = fmaf(rr[ea1], rr[eb1], sacc1);
+            }
         }
     }
     // ---- this block's sums
@@ -306,21 +313,46 @@ __global__ void __launch_bounds__(kUThreads, 1) net_update_dense_kernel(const __
     if (e1_ok) out[H * F + tid + kUThreads] = sacc1;
 }
 
-// grad[i] (+)= sum over blocks (fixed order) of partials[b][i]; entry P is the loss sum -> loss_out = sum / rows
-__global__ void net_update_reduce_kernel(const float* __restrict__ partials, int n_blocks, int P, float* __restrict__ grad, int accumulate,
-                                         float inv_b, float* __restrict__ loss_out) {
+// grad[i] (+)= sum over blocks (fixed order) of partials[b][i], then the Adam step on that entry (arithmetic order of
+// torch's _single_tensor_adam, as adam_kernel in loss.cu); entry P is the loss sum -> loss_out = sum / rows.  Launched with
+// programmatic dependent launch: the Adam constants are computed while the gradient kernel drains.
+__global__ void __launch_bounds__(256) net_update_reduce_adam_kernel(const float* __restrict__ partials, int n_blocks, int P,
+                                                                     float* __restrict__ grad, int accumulate, float inv_b,
+                                                                     float* __restrict__ loss_out, float* __restrict__ params,
+                                                                     float* __restrict__ m, float* __restrict__ v,
+                                                                     int32_t* __restrict__ step_count, double lr) {
+    pdl_release();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const double b1 = 0.9, b2 = 0.999;
+    pdl_wait();
     if (i > P) return;
     float s = 0.f;
     for (int b = 0; b < n_blocks; ++b) s += partials[(size_t)b * (P + 1) + i];
-    if (i == P) *loss_out = s * inv_b;
-    else grad[i] = accumulate ? grad[i] + s : s;
+    if (i == P) {
+        *loss_out = s * inv_b;
+        return;
+    }
+    const float g = accumulate ? grad[i] + s : s;
+    grad[i] = g;
+    const int t = *step_count + 1;                         // bumped by net_update_bump_kernel afterwards
+    const double bc1 = 1.0 - pow(b1, (double)t), bc2 = 1.0 - pow(b2, (double)t);
+    const float step_size = (float)(lr / bc1), bc2_sqrt = (float)sqrt(bc2);
+    const float w1 = (float)(1.0 - b1), w2 = (float)(1.0 - b2), b2f = (float)b2, eps = 1e-8f;
+    const float mi = m[i] + (g - m[i]) * w1;
+    const float vi = v[i] * b2f + w2 * g * g;
+    m[i] = mi;
+    v[i] = vi;
+    params[i] = params[i] - step_size * (mi / (sqrtf(vi) / bc2_sqrt + eps));
+}
+__global__ void net_update_bump_kernel(int32_t* step_count) {
+    pdl_prologue();
+    if (threadIdx.x == 0 && blockIdx.x == 0) *step_count += 1;
 }
 
 size_t dense_smem_bytes(int F, int O) {
     const MlpLayout L(F, O);
     const int n_small = L.P - H * F;
-    return 128 + (size_t)kUStages * kURows * F * 4 + (size_t)((n_small + 3) & ~3) * 4 + (size_t)kURows * kRec * 4;
+    return 128 + (size_t)kUStages * kURows * F * 4 + (size_t)((n_small + 3) & ~3) * 4 + (size_t)2 * kURows * kRec * 4;
 }
 bool dense_applicable(const float* x, int64_t rows, int F, int O) {
     return x && rows >= 1024 && F >= 64 && F <= 32 * kUTF && (F & 3) == 0 && O <= kUOMax && ((uintptr_t)x & 15) == 0 &&
@@ -393,9 +425,10 @@ extern "C" int ia2c_net_update(int32_t kind, float* params, float* grad, float* 
             net_update_dense_kernel<1><<<grid, kUThreads, smem, s>>>(A);
         }
         if ((rc = check_launch("net_update_dense_kernel"))) return rc;
-        net_update_reduce_kernel<<<ceil_div(P + 1, 256), 256, 0, s>>>(A.partials, grid, P, grad, accumulate, A.inv_b, loss_out);
-        if ((rc = check_launch("net_update_reduce_kernel"))) return rc;
-        return ia2c_adam_step(params, grad, nullptr, exp_avg, exp_avg_sq, step_count, lr, 0.9, 0.999, 1e-8, 1, P, stream);
+        if ((rc = launch_pdl("net_update_reduce_adam_kernel", net_update_reduce_adam_kernel, dim3(ceil_div(P + 1, 256)), dim3(256), 0, s,
+                             A.partials, grid, P, grad, accumulate, A.inv_b, loss_out, params, exp_avg, exp_avg_sq, step_count, lr)))
+            return rc;
+        return launch_pdl("net_update_bump_kernel", net_update_bump_kernel, dim3(1), dim3(32), 0, s, step_count);
     }
     if (x) rc = ia2c_mlp_forward(params, x, y, h1, rows, F, O, 1, softmax, stream);
     else rc = ia2c_mlp_forward_index(params, idx, y, h1, rows, F, O, softmax, stream);
