@@ -28,6 +28,20 @@ from . import _lib
 hidden_size = 6
 
 
+def _check_hidden_size():
+    """The kernels are compiled for the reference's 6-wide hidden layers (IA2C_HIDDEN, ac_nets.py:24).  A script that
+    rebinds ``hidden_size`` — here or on the ``ac_nets`` drop-in module it star-imports from — would be silently ignored;
+    refuse instead."""
+    import sys
+
+    mods = [sys.modules[__name__]] + [m for n, m in list(sys.modules.items()) if n == "ac_nets" and m is not None]
+    for m in mods:
+        v = getattr(m, "hidden_size", 6)
+        if v != 6:
+            raise _lib.IA2CError(f"{m.__name__}.hidden_size = {v!r}: libia2c_b200.so is compiled for hidden_size = 6 "
+                                 "(IA2C_HIDDEN in include/ia2c_b200.h); other widths are not supported")
+
+
 def n_params(state_dim, action_dim):
     return hidden_size * state_dim + hidden_size + hidden_size * hidden_size + hidden_size + action_dim * hidden_size + action_dim
 
@@ -205,6 +219,7 @@ class NeuralNet(nn.Module):
 
     def __init__(self, state_dim, action_dim, b_actor=False):
         super().__init__()
+        _check_hidden_size()
         dev = _device()
         self.state_dim, self.action_dim, self.b_actor = int(state_dim), int(action_dim), bool(b_actor)
         l1 = nn.Linear(state_dim, hidden_size)

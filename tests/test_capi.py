@@ -102,3 +102,15 @@ def test_unmodified_reference_scripts_resolve_against_the_drop_in_modules(script
     assert r.returncode != 0
     assert "no CPU fallback" in r.stderr, r.stderr[-2000:]
     assert "ModuleNotFoundError" not in r.stderr and "ImportError" not in r.stderr
+
+
+def test_changed_hidden_size_is_refused_not_ignored(monkeypatch):
+    """ac_nets re-exports hidden_size (the scripts star-import it); the kernels are compiled for 6 — anything else must raise."""
+    import pytest
+    from ia2c_b200 import _lib, nets
+
+    monkeypatch.setattr(nets, "hidden_size", 8)
+    with pytest.raises(_lib.IA2CError, match="hidden_size"):
+        nets._check_hidden_size()
+    monkeypatch.setattr(nets, "hidden_size", 6)
+    nets._check_hidden_size()
