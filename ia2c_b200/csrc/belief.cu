@@ -381,14 +381,31 @@ __global__ void __launch_bounds__(kThreads, 2) belief_pairs_table_kernel(const _
         const int NW = N >> 2, iw = i >> 2;
         const uint32_t sel_mix = (i & 3) == 0 ? 0x4321u : ((i & 3) == 1 ? 0x4320u : ((i & 3) == 2 ? 0x4310u : 0x4210u));
         const int words = n_envs * KQ;
-#pragma unroll 4
-        for (int x = threadIdx.x; x < words; x += blockDim.x) {
-            const int el = x / KQ, w = x - el * KQ;
-            const uint32_t lo = src[el * NW + w];
-            const uint32_t hi = (w + 1 < NW) ? src[el * NW + w + 1] : 0u;
-            uint32_t v = __byte_perm(lo, hi, w < iw ? 0x3210u : (w > iw ? 0x4321u : sel_mix));
-            if (4 * w + 3 >= K) v &= 0xFFFFFFFFu >> (8 * (4 * w + 4 - K));      // zero the padding slots
-            seen4[x] = v;
+        // (env, word) of the thread's next item, advanced without divisions; eight items' loads in flight at a time
+        const int s_el = (int)blockDim.x / KQ, s_w = (int)blockDim.x % KQ;
+        int el = (int)threadIdx.x / KQ, w = (int)threadIdx.x % KQ;
+        constexpr int kBatch = 8;
+        for (int x0 = threadIdx.x; x0 < words; x0 += kBatch * blockDim.x) {
+            uint32_t lo[kBatch], hi[kBatch];
+            int ww[kBatch];
+#pragma unroll
+            for (int b = 0; b < kBatch; ++b) {
+                const bool ok = x0 + b * (int)blockDim.x < words;
+                ww[b] = w;
+                lo[b] = ok ? __ldg(src + el * NW + w) : 0u;
+                hi[b] = (ok && w + 1 < NW) ? __ldg(src + el * NW + w + 1) : 0u;
+                el += s_el; w += s_w;
+                if (w >= KQ) { w -= KQ; ++el; }
+            }
+#pragma unroll
+            for (int b = 0; b < kBatch; ++b) {
+                const int x = x0 + b * (int)blockDim.x;
+                if (x < words) {
+                    uint32_t v = __byte_perm(lo[b], hi[b], ww[b] < iw ? 0x3210u : (ww[b] > iw ? 0x4321u : sel_mix));
+                    if (4 * ww[b] + 3 >= K) v &= 0xFFFFFFFFu >> (8 * (4 * ww[b] + 4 - K));      // zero the padding slots
+                    seen4[x] = v;
+                }
+            }
         }
     } else {
         uint8_t* seen_b = reinterpret_cast<uint8_t*>(seen4);
@@ -473,6 +490,7 @@ __global__ void __launch_bounds__(kThreads, 2) belief_pairs_table_kernel(const _
     };
 
     const int total = n_envs * KQ;
+    const bool warp_one_env = (KQ & 31) == 0;   // then total % 32 == 0 too: every warp is full and stays inside one env
     const int d_el = (int)blockDim.x / KQ, d_sq = (int)blockDim.x % KQ;
     int el = (int)threadIdx.x / KQ, sq = (int)threadIdx.x % KQ;
     uint8_t* const rec_base = P.records + ((e0 * N + i) * (int64_t)K) * IA2C_BELIEF_RECORD;   // record (e0, i, 0); block-local offsets fit 32 bits
@@ -596,9 +614,14 @@ __global__ void __launch_bounds__(kThreads, 2) belief_pairs_table_kernel(const _
                 if (w < n_valid && !(need & (1u << w))) dump(rec0 + w, out[w]);
         }
         if (FAST || P.pred_partner_out) {   // one REDUX + one shared atomic per group of lanes that share the env
-            const unsigned peers = __match_any_sync(__activemask(), el);
-            const uint32_t sum = __reduce_add_sync(peers, packed);
-            if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&counts[el], sum);
+            if (warp_one_env) {             // KQ % 32 == 0 and full warps: the whole warp works on one env
+                const uint32_t sum = __reduce_add_sync(0xffffffffu, packed);
+                if ((threadIdx.x & 31) == 0) atomicAdd(&counts[el], sum);
+            } else {
+                const unsigned peers = __match_any_sync(__activemask(), el);
+                const uint32_t sum = __reduce_add_sync(peers, packed);
+                if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&counts[el], sum);
+            }
         }
         advance(el, sq, off, &ctr);
     }
