@@ -428,10 +428,43 @@ class ActorNetwork:
         ``sample_action`` calls return them instead of the device sampler's draw (parity under replay)."""
         self._replay = iter(actions) if actions is not None else None
 
+    def _sample_small_host(self, obs):
+        """Few rows of host observations (the a2c_org_test.py loop: one env, one call per step): the kernel reads the rows from
+        and writes the actions to pinned host memory, so the call is one launch + one stream sync — no copies, no allocations."""
+        lib = _lib.load()
+        x = np.asarray(obs, dtype=np.float32)
+        F_ = self.net.state_dim
+        rows = x.size // F_
+        st = self.__dict__.get("_small")
+        if st is None or st["rows"] < rows:
+            cap = max(rows, 16)
+            hx = torch.zeros(cap * F_, dtype=torch.float32).pin_memory()
+            ha = torch.zeros(cap, dtype=torch.int64).pin_memory()
+            st = self._small = dict(rows=cap, hx=hx, ha=ha, nx=hx.numpy(), na=ha.numpy(),
+                                    probs=torch.empty(cap, self.num_outs, dtype=torch.float32, device=self.net.flat.device))
+        st["nx"][:rows * F_] = x.reshape(-1)
+        with torch.cuda.device(self.net.flat.device):
+            stream = torch.cuda.current_stream()
+            _lib.check(lib.ia2c_actor_sample(_lib.ptr(self.net.flat.detach()), st["hx"].data_ptr(), None, st["ha"].data_ptr(),
+                                             _lib.ptr(st["probs"]), rows, F_, self.num_outs, self._seed, self._calls,
+                                             stream.cuda_stream), "ia2c_actor_sample")
+            stream.synchronize()
+        self._calls += 1
+        self.last_probs = st["probs"][:rows]
+        return torch.from_numpy(st["na"][:rows].copy())
+
     def sample_action(self, obs, grad=False):
         lib = _lib.load()
         dev = self.net.flat.device
         in_dev = obs.device if isinstance(obs, torch.Tensor) else torch.device("cpu")
+        if in_dev.type == "cpu" and not _is_index_input(obs):
+            x_h = obs.detach().numpy() if isinstance(obs, torch.Tensor) else np.asarray(obs)
+            if x_h.ndim >= 1 and x_h.shape[-1] == self.net.state_dim and x_h.size <= 64 * self.net.state_dim:
+                lead = x_h.shape[:-1]
+                actions = self._sample_small_host(x_h)
+                if self._replay is not None:
+                    return torch.as_tensor(np.asarray(next(self._replay))).reshape(lead).to(torch.int64)
+                return actions.reshape(lead)
         if _is_index_input(obs):   # class indices standing for one-hot rows (index fast path)
             idx, x2 = _checked_indices(obs, self.net.state_dim, dev)
             lead, entry = idx.shape, lib.ia2c_actor_sample_index

@@ -146,8 +146,14 @@ class Org(_EnvBase):
         self._vec = OrgVecEnv(1, n_agents=2, max_episode_steps=None)
         torch = _lib.require_cuda()
         self._torch = torch
-        self._action = torch.zeros(1, dtype=torch.int32, device=self._vec.device)
-        self._h_action = torch.zeros(1, dtype=torch.int32).pin_memory()
+        # one pinned (host-mapped) line the step kernel reads the action from and writes its outputs to — a single env is
+        # pure launch latency, so there is no H2D / D2H copy and no torch op per step: action i32 @0, state i32 @4,
+        # reward f64 @8, observation f32[6] @16
+        self._h = torch.zeros(64, dtype=torch.uint8).pin_memory()
+        self._np = self._h.numpy()
+        self._np_action, self._np_state = self._np[0:4].view(np.int32), self._np[4:8].view(np.int32)
+        self._np_reward, self._np_obs = self._np[8:16].view(np.float64), self._np[16:40].view(np.float32)
+        self._h_ptr = self._h.data_ptr()
         self.done = False
         self.hist = 0
         self.action_space = _Discrete(2)          # Org.py:27 (sic)
@@ -192,15 +198,18 @@ class Org(_EnvBase):
         except Exception:
             code = int(np.asarray(action).reshape(-1)[0])
         self._push_observation()  # honour in-place edits of .observation by the caller
-        self._h_action[0] = code
-        self._action.copy_(self._h_action, non_blocking=True)
-        obs, rew, _ = self._vec.step_device(self._action)
-        packed = self._torch.cat([obs.reshape(-1).double(), rew, self._vec.state.double()]).cpu().numpy()
-        self.observation[:] = packed[:6]          # in place: the returned array is the same object (Q4)
-        self._synced_obs[:] = packed[:6]
+        v, h = self._vec, self._h_ptr
+        self._np_action[0] = code
+        with v._guard():
+            stream = self._torch.cuda.current_stream()
+            _lib.check(v.lib.ia2c_org_step_joint(_lib.ptr(v.state), _lib.ptr(v.hist), _lib.ptr(v.cls), None, h, h + 16, h + 8, None,
+                                                 h + 4, None, 1, 0, stream.cuda_stream), "ia2c_org_step_joint")
+            stream.synchronize()
+        self.observation[:] = self._np_obs        # in place: the returned array is the same object (Q4)
+        self._synced_obs[:] = self._np_obs
         valid = 0 <= code <= 8
-        self._reward = float(packed[6]) if valid else self._reward   # untouched on unknown codes (Q16)
-        self._state = int(packed[7])
+        self._reward = float(self._np_reward[0]) if valid else self._reward   # untouched on unknown codes (Q16)
+        self._state = int(self._np_state[0])
         return (self.observation, self._reward, self.done, self.done, {})
 
     def reset(self, seed=None, options={}):
