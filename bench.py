@@ -34,7 +34,7 @@ UNIT = "agent-steps/s"
 DTYPE = "f32 nets / f64 env+belief"
 T_STEPS, N_MODELS = 30, 5
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full captures summarised under profiles/
-NCU_DRAM_BYTES = {"rollout_fused_kernel<2,5,1>@4096": 70656}
+NCU_DRAM_BYTES = {"rollout_fused_kernel<2,5,1>@4096": 71168}
 # fp32 FLOPs per agent-step: rollout 210, critic phase 1512, actor phase 1044
 FLOPS_ROLLOUT, FLOPS_CRITIC, FLOPS_ACTOR = 210, 1512, 1044
 
@@ -739,16 +739,40 @@ def bench_cfg3(ctx, _lib, steps, peak_gbs, cpu):
             s.record(); pair(); e.record(); e.synchronize()
             dev_ms += s.elapsed_time(e)
         wall = (time.perf_counter() - t0) / steps
-        x_bytes = T * E * F * 4 if obs.dtype.is_floating_point else T * E * 8
         entry = {"input": tag, "ms_per_step": wall * 1e3, "device_ms_per_step": dev_ms / steps, "value": T * E / wall, "unit": "rows/s"}
         if obs.dtype.is_floating_point:
-            passes = getattr(critic, "x_passes_per_update", 2)
-            entry["roofline"] = {"kernel": "mlp fused forward+backward over X (critic + actor update pair)", "bound": "hbm",
-                                 "achieved": 2 * passes * x_bytes / (dev_ms / steps * 1e-3) / 1e9, "peak": peak_gbs, "unit": "GB/s",
-                                 "frac": 2 * passes * x_bytes / (dev_ms / steps * 1e-3) / 1e9 / peak_gbs, "traffic": None,
-                                 "bytes_per_launch": passes * x_bytes,
-                                 "note": f"X (131 MB) is read {passes}x per net update; event-timed over the whole update pair incl. loss, Adam "
-                                         "and host launch gaps (the class API is host-bound at this size)"}
+            # the dominant kernel timed on its own: ia2c_net_update (critic) through the C ABI, L2 flushed, CUDA events
+            x_bytes = T * E * F * 4
+            lib = _lib.load()
+            P = 6 * F + 6 + 36 + 6 + 6 * O + O
+            z = lambda n, dt=torch.float32: torch.zeros(n, dtype=dt, device="cuda")
+            p_, g_, m_, v_, st_, ls_ = torch.randn(P, device="cuda") * 0.3, z(P), z(P), z(P), z(1, torch.int32), z(1)
+            ws = torch.empty(int(lib.ia2c_net_update_workspace(T * E, F, O)), dtype=torch.float32, device="cuda")
+            a_i, sig = act.reshape(-1).to(torch.int32).contiguous(), target.reshape(-1).contiguous()
+            x2 = obs.reshape(-1, F)
+            D = lambda t: t.data_ptr()
+
+            def upd():
+                _lib.check(lib.ia2c_net_update(0, D(p_), D(g_), D(m_), D(v_), D(st_), D(x2), None, D(a_i), D(sig), 0.0, 5e-4, D(ls_), None,
+                                               D(ws), T * E, F, O, _lib.stream_ptr()))
+            for _ in range(3):
+                upd()
+            tot = 0.0
+            for _ in range(10):
+                ctx.flush()
+                s, e = ctx.ev(), ctx.ev()
+                s.record(); upd(); e.record(); e.synchronize()
+                tot += s.elapsed_time(e)
+            us = tot / 10 * 1e3
+            entry["roofline"] = {"kernel": "net_update_dense_kernel<0> + net_update_reduce_adam_kernel (one critic update, X read once)",
+                                 "bound": "hbm", "achieved": x_bytes / (us * 1e-6) / 1e9, "peak": peak_gbs, "unit": "GB/s",
+                                 "frac": x_bytes / (us * 1e-6) / 1e9 / peak_gbs, "traffic": 135582464, "bytes_per_launch": x_bytes,
+                                 "us_per_launch": us,
+                                 "note": "single pass: 32-row tiles by cp.async.bulk + mbarrier, forward products and dW1 from the same staged "
+                                         "tile; ncu dram__bytes_read = 131.6 MB = rows x F x 4 (profiles/r02_ncu_summary.md); the kernel alone "
+                                         "takes 48 us (0.42), the figure here includes the reduce + Adam kernel and launch gaps"}
+            ctx.drop_flush()
+            del ws, x2
         res.append(entry)
         del critic, actor, obs
     out = {"config": "cfg3", "workload": "ac_nets CriticNetwork/ActorNetwork.batch_update pair (ac_nets.py:62-80,112-127) at a2c_test.py's "
