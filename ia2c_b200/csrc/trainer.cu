@@ -284,18 +284,33 @@ __global__ void __launch_bounds__(kGradThreads) actor_grad_kernel(ia2c_episode_d
             float2 h1[3], h2[3];
             fwd_f2<J>(wc, x, h1, h2, q);
         }
+        // The row's inputs are fetched ONE ITERATION AHEAD (the kernel was stalled on these L2 round trips: ncu long_scoreboard
+        // 1.8 per issue): iteration t consumes {next observation, next own action, next predicted partner, reward} loaded
+        // during iteration t-1 and carries its own action / predicted partner over from the previous row.
+        struct RowIn { float xn[kIn]; int own_n, pp_n; float rew; };
+        auto fetch = [&](int t, RowIn& in) {
+            const int64_t r = (int64_t)t * E + e;
+            load_obs6(d.obs + (r + E) * kIn, in.xn);                 // next_obs[t] = obs[t+1]
+            in.own_n = d.act[(r + E) * N + n];
+            in.pp_n = d.partner_pred[(r + E) * N + n];
+            in.rew = d.reward[r];
+        };
+        RowIn cur;
+        fetch(t0, cur);
+        int own = d.act[((int64_t)t0 * E + e) * N + n], pp = d.partner_pred[((int64_t)t0 * E + e) * N + n];
         for (int t = t0; t < t1; ++t) {
             const int64_t r = (int64_t)t * E + e;
-            float xn[kIn], qn[J];
-            load_obs6(d.obs + (r + E) * kIn, xn);
+            RowIn nxt = cur;
+            if (t + 1 < t1) fetch(t + 1, nxt);
+            float qn[J];
             {
                 float2 h1[3], h2[3];
-                fwd_f2<J>(wc, xn, h1, h2, qn);                       // UPDATED critic, no gradient (ia2c.py:116-127)
+                fwd_f2<J>(wc, cur.xn, h1, h2, qn);                   // UPDATED critic, no gradient (ia2c.py:116-127)
             }
-            const int own = d.act[r * N + n], own_n = d.act[(r + E) * N + n];
-            const int ja = joint_index(n, N, own, d.partner_pred[r * N + n]);            // ia2c.py:120-121
-            const int nja = joint_index(n, N, own_n, d.partner_pred[(r + E) * N + n]);
-            const float adv = (d.reward[r] + d.gamma * select_out<J>(qn, nja)) - select_out<J>(q, ja);
+            const int own_n = cur.own_n;
+            const int ja = joint_index(n, N, own, pp);                                   // ia2c.py:120-121
+            const int nja = joint_index(n, N, own_n, cur.pp_n);
+            const float adv = (cur.rew + d.gamma * select_out<J>(qn, nja)) - select_out<J>(q, ja);
             if (d.adv_dump) d.adv_dump[(int64_t)n * rows + r] = adv;
             float2 h1[3], h2[3];
             float p[A];
@@ -327,9 +342,12 @@ __global__ void __launch_bounds__(kGradThreads) actor_grad_kernel(ia2c_episode_d
             for (int o = 0; o < A; ++o) dy[o] = qq[o] * (gq[o] - qg) * inv_b;   // through normalise + softmax
             bwd_f2<A>(w, x, h1, h2, [&](int o) { return dy[o]; }, g2);
 #pragma unroll
-            for (int k = 0; k < kIn; ++k) x[k] = xn[k];
+            for (int k = 0; k < kIn; ++k) x[k] = cur.xn[k];
 #pragma unroll
             for (int o = 0; o < J; ++o) q[o] = qn[o];
+            own = own_n;
+            pp = cur.pp_n;
+            cur = nxt;
         }
     }
     float g[2 * GN];
