@@ -41,7 +41,7 @@ def install_dropins():
 
 def substitute(src, settings, fname="<script>"):
     for name, value in settings.items():
-        src, n = re.subn(rf"^{re.escape(name)}\s*=\s*[^\n#]+", f"{name} = {value}", src, count=1, flags=re.M)
+        src, n = re.subn(rf"^{re.escape(name)}\s*=\s*[^\n#]+?(?=\s*(?:#|$))", f"{name} = {value}", src, count=1, flags=re.M)
         if n != 1:
             raise ValueError(f"{fname}: no module-level assignment of {name!r} to rewrite")
     return src
