@@ -663,7 +663,7 @@ __global__ void __launch_bounds__(kThreads, 2) belief_pairs_table_kernel(const _
 
 template <int M>
 int launch_pairs_table(PairsArgs& P, cudaStream_t stream) {
-    P.envs_per_block = std::max(1, std::min(128, 32768 / P.K));   // amortise the table build and the staging of the others' actions
+    P.envs_per_block = std::max(1, std::min(64, 16384 / P.K));   // amortise the table build and the staging of the others' actions
     const int64_t env_blocks = (P.E + P.envs_per_block - 1) / P.envs_per_block;
     size_t smem = (104 + 3 * M * 101 + M * 3) * sizeof(double) + (((3 * M * 101 + 3) & ~3) + ((2 * M + 3) & ~3)) * sizeof(float) +
                   (size_t)P.envs_per_block * sizeof(uint32_t) + kExactQueue * sizeof(uint16_t) +
