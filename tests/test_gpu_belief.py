@@ -114,3 +114,37 @@ def test_pairs_kernel_vs_oracle(E, N, M):
         assert np.array_equal(host(rec)[..., :M], B.to_hundredths(obp)) and np.array_equal(host(rec)[..., 6], oap)
         assert np.array_equal(host(partner), mode3(oap))
         prior = obp
+
+
+def test_pairs_fast_path_vs_oracle_at_scale():
+    """The steady-state template of the many-agent kernel (device Philox, no dumps: FAST) on 1.5 M records per step against the
+    oracle: every stored posterior byte and every predicted action — i.e. every fp32-screened decision and every record deferred
+    to the exact pass — must equal the reference's fp64 sequence."""
+    import torch
+    from ia2c_b200 import _lib
+    lib = _lib.load()
+    E, N, M = 96, 128, 5
+    K = N - 1
+    rng = np.random.RandomState(5)
+    fa = rng.rand(N, M, 3)
+    fa /= fa.sum(-1, keepdims=True)
+    rec = torch.zeros(E, N, K, 8, dtype=torch.uint8, device="cuda")
+    partner = torch.empty(E, N, dtype=torch.uint8, device="cuda")
+    fa_d = dev(fa)
+    prior = np.tile(B.uniform_prior(1, M)[0], (E, N, K, 1))
+    rows = (np.arange(E)[:, None] + 7) * N + np.arange(N)[None, :]
+    for t in range(4):
+        act = rng.randint(0, 3, size=(E, N)).astype(np.uint8)
+        if t == 0:   # start from the uniform prior through the non-FAST template (reset), then three FAST steps
+            u = P.belief_uniforms(3, 9, t, rows, K)
+            _lib.check(lib.ia2c_belief_update_pairs(_lib.ptr(rec), _lib.ptr(fa_d), dptr(act), None, None, None, _lib.ptr(partner), E, N, M, 1,
+                                                    3, 9, t, 7, _lib.stream_ptr()))
+        else:
+            u = P.belief_uniforms(3, 9, t, rows, K)
+            _lib.check(lib.ia2c_belief_update_pairs(_lib.ptr(rec), _lib.ptr(fa_d), dptr(act), None, None, None, _lib.ptr(partner), E, N, M, 0,
+                                                    3, 9, t, 7, _lib.stream_ptr()))
+        oap, obp = _pairs_oracle(fa, act, prior, u)
+        r = host(rec)
+        assert np.array_equal(r[..., :M], B.to_hundredths(obp)) and np.array_equal(r[..., 6], oap) and not r[..., 7].any()
+        assert np.array_equal(host(partner), mode3(oap))
+        prior = obp
