@@ -19,6 +19,7 @@ FLAG_SKIP_ADAM = 2
 FLAG_FUSED_CRITIC = 4
 FLAG_GRAD_ONLY = 8
 FLAG_ACTOR_COLUMNS = 16
+FLAG_BELIEF_PER_STEP = 32
 BELIEF_RECORD = 8
 ABI_VERSION = 2
 ACTOR_P = 105
@@ -67,6 +68,8 @@ SIGNATURES = {
     "ia2c_org_step_agents": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, vp]),
     "ia2c_belief_update_dense": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, vp]),
     "ia2c_belief_update_pairs": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, u64, u32, u32, i64, vp]),
+    "ia2c_belief_supports_episode": (C.c_int, [i32, i32]),
+    "ia2c_belief_update_pairs_episode": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, u64, u32, i64, vp]),
     "ia2c_debug_divide": (C.c_int, [vp, vp, vp, vp, i64, vp]),
     "ia2c_debug_fp32_peak": (C.c_int, [vp, i32, i32, i32, C.POINTER(f64), vp]),
     "ia2c_mlp_forward": (C.c_int, [vp, vp, vp, vp, i64, i32, i32, i32, i32, vp]),

@@ -682,6 +682,361 @@ int launch_pairs_table(PairsArgs& P, cudaStream_t stream) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Whole-episode pairwise update for many modelled others (K >= 32): the trainer's rollout.
+//
+// During a rollout nothing reads a belief before the update phase: the env and the actors depend on the sampled actions
+// only (ia2c.py:72-102 — the filter's predicted action enters the critic's index at ia2c.py:104-121, after the episode).
+// The rollout therefore runs its T+1 env / actor steps first and then updates every belief record through ALL T+1 steps in
+// ONE kernel with the record resident in registers: the 16 bytes per update that belief_pairs_table_kernel streams per step
+// (8-byte record read + written) shrink to one 8-byte store per EPISODE, and the byte unpack / pack, the address arithmetic,
+// the cp.async ring and the table build are paid once per record-episode instead of once per update.  Same screen, same
+// exact sequence, same Philox counters as the per-step kernel: bit-identical records, predictions and partner modes
+// (tests/test_gpu_belief.py compares the two kernels and the oracle).
+// Block = (agent, chunk of envs) with <= 4 quads (16 records) per thread; per step: stage the others' actions (double
+// buffered), screen, defer the ~0.3 % flagged records to a dense exact pass that PATCHES the owners' registers before the
+// next step, reduce the predicted-action counts per env, write partner_pred[t].
+struct EpisodePairsArgs {
+    uint8_t* records;              // [E,N,K,8] out: the posteriors after step T (+ predicted action of step T in byte 6)
+    const double* filter_action;   // [N,M,3]
+    const uint8_t* act;            // [T1,E,N] sampled actions of every step
+    const double* u_injected;      // [T1,E,N,K] or null
+    uint8_t* pred_dump;            // [T1,E,N,K] or null
+    uint8_t* belief_dump;          // [T1,E,N,K,M] or null
+    uint8_t* partner_pred;         // [T1,E,N]
+    int64_t E, env_offset;
+    int N, K, T1, envs_per_block;
+    uint32_t episode;
+    uint32_t rk[20];
+};
+constexpr int kEpQuads = 4;        // quads per thread
+constexpr int kEpQueue = 512;      // deferred records per block and step
+
+template <int M, bool FAST>
+__global__ void __launch_bounds__(kThreads, 2) belief_pairs_episode_kernel(const __grid_constant__ EpisodePairsArgs P) {
+    constexpr int A = IA2C_AGENT_ACTIONS;
+    const double* const u_injected = FAST ? nullptr : P.u_injected;
+    uint8_t* const belief_dump = FAST ? nullptr : P.belief_dump;
+    uint8_t* const pred_dump = FAST ? nullptr : P.pred_dump;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int queue_n;
+    const int N = P.N, K = P.K, i = blockIdx.y;
+    const int KQ = (K + 3) >> 2;
+    const int EC = P.envs_per_block;
+    const int64_t e0 = (int64_t)blockIdx.x * EC;
+    const int n_envs = (int)min((int64_t)EC, P.E - e0);
+    const int lane = threadIdx.x & 31;
+    double* tab = reinterpret_cast<double*>(smem_raw);               // [104]   k/100
+    double* bpt = tab + 104;                                         // [A][M][101]
+    double* fa = bpt + A * M * 101;                                  // [M][A]
+    float* bpt32 = reinterpret_cast<float*>(fa + M * A);             // [A][M][101]
+    float* fcum = bpt32 + ((A * M * 101 + 3) & ~3);                  // [2][M]: F[m][0], F[m][0]+F[m][1]
+    uint32_t* counts = reinterpret_cast<uint32_t*>(fcum + ((2 * M + 3) & ~3));   // [EC] packed 3 x 10 bits
+    uint4* queue = reinterpret_cast<uint4*>(counts + ((EC + 3) & ~3));           // [kEpQueue] {raw.x, raw.y, word or u index, seen | result}
+    uint32_t* seen4 = reinterpret_cast<uint32_t*>(queue + kEpQueue);              // [2][EC][KQ] the others' actions, double-buffered
+    pdl_release();
+    for (int k = threadIdx.x; k <= 100; k += blockDim.x) tab[k] = __ddiv_rn((double)k, 100.0);
+    for (int k = threadIdx.x; k < M * A; k += blockDim.x) fa[k] = P.filter_action[(int64_t)i * M * A + k];
+    if (threadIdx.x == 0) queue_n = 0;
+    __syncthreads();
+    for (int x = threadIdx.x; x < A * M * 101; x += blockDim.x) {
+        const int seen = x / (M * 101), m = (x / 101) % M, k = x % 101;
+        const double p = tab[k];
+        double acc = __dmul_rn(seen == 0 ? 0.8 : 0.1, __dmul_rn(fa[m * A + 0], p));
+#pragma unroll
+        for (int a = 1; a < A; ++a) acc = __dadd_rn(acc, __dmul_rn(seen == a ? 0.8 : 0.1, __dmul_rn(fa[m * A + a], p)));
+        bpt[x] = acc;
+        bpt32[x] = (float)acc;
+    }
+    if (threadIdx.x < M) {
+        fcum[threadIdx.x] = (float)fa[threadIdx.x * A];
+        fcum[M + threadIdx.x] = (float)__dadd_rn(fa[threadIdx.x * A], fa[threadIdx.x * A + 1]);
+    }
+    pdl_wait();
+    __syncthreads();
+    float f0[M], f01[M];
+#pragma unroll
+    for (int m = 0; m < M; ++m) { f0[m] = fcum[m]; f01[m] = fcum[M + m]; }
+    const uint32_t bpt32_s = (uint32_t)__cvta_generic_to_shared(bpt32);
+    const float2 magic2 = make_float2(kRoundMagic, kRoundMagic), minus1 = make_float2(-1.f, -1.f);
+
+    // fp32 screen of two records (see belief_pairs_table_kernel) -> packed records, bit w set when record w needs the exact path
+    auto screen_pair = [&](uint32_t seenA, uint32_t seenB, float ufA, float ufB, uint2 rawA, uint2 rawB, uint2& outA, uint2& outB) -> uint32_t {
+        const uint32_t rowA = bpt32_s + seenA * (M * 101 * 4), rowB = bpt32_s + seenB * (M * 101 * 4);
+        float2 bp[M];
+#pragma unroll
+        for (int m = 0; m < M; ++m) {
+            const uint32_t sel = 0x4440u | (uint32_t)(m & 3);
+            const uint32_t kA = __byte_perm(m < 4 ? rawA.x : rawA.y, 0u, sel), kB = __byte_perm(m < 4 ? rawB.x : rawB.y, 0u, sel);
+            bp[m] = make_float2(lds_f32(rowA + 4u * kA + (uint32_t)(m * 101 * 4)), lds_f32(rowB + 4u * kB + (uint32_t)(m * 101 * 4)));
+        }
+        float2 S = bp[0];
+#pragma unroll
+        for (int m = 1; m < M; ++m) S = __fadd2_rn(S, bp[m]);
+        float rA, rB;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rA) : "f"(S.x));
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rB) : "f"(S.y));
+        const float2 r100 = __fmul2_rn(make_float2(rA, rB), make_float2(100.f, 100.f));
+        float2 kf[M];
+        float dmaxA = 0.f, dmaxB = 0.f;
+#pragma unroll
+        for (int m = 0; m < M; ++m) {
+            kf[m] = __ffma2_rn(bp[m], r100, magic2);
+            const float2 nk = __ffma2_rn(kf[m], minus1, magic2);
+            const float2 d = __ffma2_rn(bp[m], r100, nk);
+            dmaxA = fmaxf(dmaxA, fabsf(d.x));
+            dmaxB = fmaxf(dmaxB, fabsf(d.y));
+        }
+        float2 c0 = __fmul2_rn(bp[0], make_float2(f0[0], f0[0])), c1 = __fmul2_rn(bp[0], make_float2(f01[0], f01[0]));
+#pragma unroll
+        for (int m = 1; m < M; ++m) {
+            c0 = __ffma2_rn(bp[m], make_float2(f0[m], f0[m]), c0);
+            c1 = __ffma2_rn(bp[m], make_float2(f01[m], f01[m]), c1);
+        }
+        const float2 uS = __fmul2_rn(make_float2(ufA, ufB), S);
+        const float2 win = __fmul2_rn(S, make_float2(kCdfWindow, kCdfWindow));
+        const float2 g0 = __ffma2_rn(c0, minus1, uS), g1 = __ffma2_rn(c1, minus1, uS);
+        const uint32_t apA = uS.x < c0.x ? 0u : (uS.x < c1.x ? 1u : 2u), apB = uS.y < c0.y ? 0u : (uS.y < c1.y ? 1u : 2u);
+        const bool exA = (dmaxA > kHalfWindow) | (fminf(fabsf(g0.x), fabsf(g1.x)) < win.x) | (ufA > 1.f - 2e-5f);
+        const bool exB = (dmaxB > kHalfWindow) | (fminf(fabsf(g0.y), fabsf(g1.y)) < win.y) | (ufB > 1.f - 2e-5f);
+        auto pack = [&](bool second, uint32_t ap) -> uint2 {
+            uint32_t kb[M];
+#pragma unroll
+            for (int m = 0; m < M; ++m) kb[m] = __float_as_uint(second ? kf[m].y : kf[m].x);
+            uint2 out;
+            out.x = __byte_perm(__byte_perm(kb[0], kb[1 < M ? 1 : 0], 0x0040u), __byte_perm(kb[2 < M ? 2 : 0], kb[3 < M ? 3 : 0], 0x0040u), 0x5410u);
+            if (M < 4) out.x &= (M == 2 ? 0xFFFFu : 0xFFFFFFu);
+            out.y = M > 5 ? __byte_perm(__byte_perm(kb[M > 4 ? 4 : 0], kb[M > 5 ? 5 : 0], 0x0040u), ap, 0x5410u)
+                          : (M > 4 ? __byte_perm(kb[M > 4 ? 4 : 0], ap, 0x5450u) : ap << 16);
+            return out;
+        };
+        outA = pack(false, apA);
+        outB = pack(true, apB);
+        return (exA ? 1u : 0u) | (exB ? 2u : 0u);
+    };
+
+    // ---- the thread's quads (fixed for the whole episode) and their state
+    const int total = n_envs * KQ;
+    const bool warp_one_env = (KQ & 31) == 0;
+    const int prior_k = (int)rint(100.0 / M);
+    uint2 prior;
+    prior.x = (uint32_t)prior_k * (M >= 4 ? 0x01010101u : (M == 3 ? 0x010101u : 0x0101u));
+    prior.y = M > 4 ? (uint32_t)prior_k * (M > 5 ? 0x0101u : 0x01u) : 0u;
+    int q_el[kEpQuads], q_sq[kEpQuads];
+    uint2 st[kEpQuads][4];
+#pragma unroll
+    for (int s_ = 0; s_ < kEpQuads; ++s_) {
+        const int q = (int)threadIdx.x + s_ * (int)blockDim.x;
+        q_el[s_] = q < total ? q / KQ : -1;
+        q_sq[s_] = q < total ? q % KQ : 0;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) st[s_][w] = prior;
+    }
+    const uint64_t ctr0 = (uint64_t)((P.env_offset + e0) * N + i) * (uint64_t)KQ;
+    const uint32_t row_ctr = (uint32_t)N * (uint32_t)KQ;
+    // staging of the others' actions of one step (own action skipped, 4 slots per word); requires N % 4 == 0 (checked by the host)
+    const int NW = N >> 2, iw = i >> 2;
+    const uint32_t sel_mix = (i & 3) == 0 ? 0x4321u : ((i & 3) == 1 ? 0x4320u : ((i & 3) == 2 ? 0x4310u : 0x4210u));
+    uint32_t stage_lo[kEpQuads], stage_hi[kEpQuads];
+    auto stage_load = [&](int t) {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(P.act + ((int64_t)t * P.E + e0) * N);
+#pragma unroll
+        for (int s_ = 0; s_ < kEpQuads; ++s_) {
+            const bool ok = q_el[s_] >= 0;
+            stage_lo[s_] = ok ? __ldg(src + q_el[s_] * NW + q_sq[s_]) : 0u;
+            stage_hi[s_] = (ok && q_sq[s_] + 1 < NW) ? __ldg(src + q_el[s_] * NW + q_sq[s_] + 1) : 0u;
+        }
+    };
+    auto stage_store = [&](int buf) {
+#pragma unroll
+        for (int s_ = 0; s_ < kEpQuads; ++s_) {
+            if (q_el[s_] >= 0) {
+                const int w = q_sq[s_];
+                uint32_t v = __byte_perm(stage_lo[s_], stage_hi[s_], w < iw ? 0x3210u : (w > iw ? 0x4321u : sel_mix));
+                if (4 * w + 3 >= K) v &= 0xFFFFFFFFu >> (8 * (4 * w + 4 - K));
+                seen4[buf * (EC * KQ) + q_el[s_] * KQ + w] = v;
+            }
+        }
+    };
+    stage_load(0);
+    stage_store(0);
+    for (int k = threadIdx.x; k < n_envs; k += blockDim.x) counts[k] = 0u;
+    __syncthreads();
+
+    for (int t = 0; t < P.T1; ++t) {
+        const int buf = t & 1;
+        if (t + 1 < P.T1) stage_load(t + 1);                       // next step's actions: in flight during this step's arithmetic
+        const uint32_t c2 = ((uint32_t)t & 0xFFFFu) | (kStreamBelief << 16);
+        uint32_t need16 = 0u;
+#pragma unroll
+        for (int s_ = 0; s_ < kEpQuads; ++s_) {
+            const int el = q_el[s_], sq = q_sq[s_];
+            const bool live = el >= 0;
+            const int jj0 = 4 * sq;
+            const int n_valid = live ? min(4, K - jj0) : 0;
+            const int64_t rec0 = ((e0 + (live ? el : 0)) * N + i) * (int64_t)K + jj0;
+            const int64_t trec0 = (int64_t)t * P.E * N * K + rec0;      // index into the per-step tapes / dumps
+            uint32_t words[4] = {0u, 0u, 0u, 0u};
+            if (!u_injected) {
+                const uint64_t index = ctr0 + (uint32_t)(live ? el : 0) * row_ctr + (uint32_t)sq;
+                const uint4 rnd = philox4x32_10_rk(make_uint4((uint32_t)index, (uint32_t)(index >> 32), c2, P.episode), P.rk);
+                words[0] = rnd.x; words[1] = rnd.y; words[2] = rnd.z; words[3] = rnd.w;
+            }
+            const uint32_t seen_w = live ? seen4[buf * (EC * KQ) + el * KQ + sq] : 0u;
+            float uf[4];
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+                if (u_injected) uf[w] = n_valid ? (float)u_injected[trec0 + min(w, n_valid - 1)] : 0.f;
+                else uf[w] = __uint_as_float(0x3F800000u | (words[w] >> 9)) - 1.0f;
+            }
+            uint2 out[4];
+            uint32_t need = screen_pair(__byte_perm(seen_w, 0u, 0x4440u), __byte_perm(seen_w, 0u, 0x4441u), uf[0], uf[1], st[s_][0], st[s_][1], out[0], out[1]);
+            need |= screen_pair(__byte_perm(seen_w, 0u, 0x4442u), __byte_perm(seen_w, 0u, 0x4443u), uf[2], uf[3], st[s_][2], st[s_][3], out[2], out[3]) << 2;
+            need &= (1u << n_valid) - 1u;
+            uint32_t packed = 0u;
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+                if (w < n_valid && !(need & (1u << w))) {
+                    st[s_][w] = out[w];
+                    packed += 1u << (10u * (out[w].y >> 16));
+                    if (belief_dump) {
+#pragma unroll
+                        for (int m = 0; m < M; ++m) belief_dump[(trec0 + w) * M + m] = (uint8_t)(((m < 4 ? out[w].x : out[w].y) >> (8 * (m & 3))) & 0xFFu);
+                    }
+                    if (pred_dump) pred_dump[trec0 + w] = (uint8_t)(out[w].y >> 16);
+                }
+            }
+            need16 |= need << (4 * s_);
+            if (warp_one_env) {
+                const uint32_t sum = __reduce_add_sync(0xffffffffu, packed);
+                if (lane == 0 && live) atomicAdd(&counts[el], sum);
+            } else {
+                const unsigned peers = __match_any_sync(0xffffffffu, el);
+                const uint32_t sum = __reduce_add_sync(peers, packed);
+                if (lane == __ffs(peers) - 1 && live) atomicAdd(&counts[el], sum);
+            }
+        }
+        // ---- deferred exact pass: flagged records -> queue -> dense fp64 sequence -> owners patch their registers
+        int qbase = 0;
+        if (need16) {
+            qbase = atomicAdd(&queue_n, __popc(need16));
+            int pos = qbase;
+#pragma unroll
+            for (int s_ = 0; s_ < kEpQuads; ++s_) {
+#pragma unroll
+                for (int w = 0; w < 4; ++w) {
+                    if (need16 & (1u << (4 * s_ + w))) {
+                        const uint32_t seen = (seen4[buf * (EC * KQ) + q_el[s_] * KQ + q_sq[s_]] >> (8 * w)) & 0xFFu;
+                        const uint32_t code = ((uint32_t)(q_el[s_] * KQ + q_sq[s_]) << 2) | (uint32_t)w;   // quad << 2 | slot
+                        if (pos < kEpQueue) queue[pos] = make_uint4(st[s_][w].x, st[s_][w].y, code, seen);
+                        ++pos;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        const int n_def = min(queue_n, kEpQueue);
+        for (int x = threadIdx.x; x < n_def; x += blockDim.x) {
+            const uint4 en = queue[x];
+            const int q = (int)(en.z >> 2), w = (int)(en.z & 3u);
+            const int el_ = q / KQ, sq_ = q - el_ * KQ;
+            double u;
+            if (u_injected) {
+                u = u_injected[(int64_t)t * P.E * N * K + ((e0 + el_) * N + i) * (int64_t)K + 4 * sq_ + w];
+            } else {
+                const uint64_t index = ctr0 + (uint32_t)el_ * row_ctr + (uint32_t)sq_;
+                const uint4 rnd = philox4x32_10_rk(make_uint4((uint32_t)index, (uint32_t)(index >> 32), c2, P.episode), P.rk);
+                u = belief_word_to_unit_f64(w == 0 ? rnd.x : (w == 1 ? rnd.y : (w == 2 ? rnd.z : rnd.w)));
+            }
+            const uint2 res = belief_exact_record<M>(bpt + en.w * (M * 101), fa, make_uint2(en.x, en.y), -1, u);
+            queue[x] = make_uint4(res.x, res.y, en.z, en.w);
+        }
+        __syncthreads();
+        if (need16) {
+            int pos = qbase;
+#pragma unroll
+            for (int s_ = 0; s_ < kEpQuads; ++s_) {
+#pragma unroll
+                for (int w = 0; w < 4; ++w) {
+                    if (need16 & (1u << (4 * s_ + w))) {
+                        uint2 res;
+                        if (pos < kEpQueue) {
+                            const uint4 en = queue[pos];
+                            res = make_uint2(en.x, en.y);
+                        } else {   // queue full (never seen in practice): the exact sequence right here
+                            const uint32_t seen = (seen4[buf * (EC * KQ) + q_el[s_] * KQ + q_sq[s_]] >> (8 * w)) & 0xFFu;
+                            const int64_t trec = (int64_t)t * P.E * N * K + ((e0 + q_el[s_]) * N + i) * (int64_t)K + 4 * q_sq[s_] + w;
+                            double u;
+                            if (u_injected) {
+                                u = u_injected[trec];
+                            } else {
+                                const uint64_t index = ctr0 + (uint32_t)q_el[s_] * row_ctr + (uint32_t)q_sq[s_];
+                                const uint4 rnd = philox4x32_10_rk(make_uint4((uint32_t)index, (uint32_t)(index >> 32), c2, P.episode), P.rk);
+                                u = belief_word_to_unit_f64(w == 0 ? rnd.x : (w == 1 ? rnd.y : (w == 2 ? rnd.z : rnd.w)));
+                            }
+                            res = belief_exact_record<M>(bpt + seen * (M * 101), fa, st[s_][w], -1, u);
+                        }
+                        ++pos;
+                        st[s_][w] = res;
+                        atomicAdd(&counts[q_el[s_]], 1u << (10u * (res.y >> 16)));
+                        if (belief_dump || pred_dump) {
+                            const int64_t trec = (int64_t)t * P.E * N * K + ((e0 + q_el[s_]) * N + i) * (int64_t)K + 4 * q_sq[s_] + w;
+                            if (belief_dump) {
+#pragma unroll
+                                for (int m = 0; m < M; ++m) belief_dump[trec * M + m] = (uint8_t)(((m < 4 ? res.x : res.y) >> (8 * (m & 3))) & 0xFFu);
+                            }
+                            if (pred_dump) pred_dump[trec] = (uint8_t)(res.y >> 16);
+                        }
+                    }
+                }
+            }
+        }
+        if (t + 1 < P.T1) stage_store(buf ^ 1);                    // nobody reads that buffer during this step
+        __syncthreads();
+        // ---- partner mode of step t, reset for the next step
+        for (int x = threadIdx.x; x < n_envs; x += blockDim.x) {
+            const uint32_t c = counts[x];
+            const int n0 = c & 1023, n1 = (c >> 10) & 1023, n2 = c >> 20;
+            int best = 0, bc = n0;
+            if (n1 > bc) { best = 1; bc = n1; }
+            if (n2 > bc) best = 2;                                   // ties -> lowest action
+            P.partner_pred[((int64_t)t * P.E + e0 + x) * N + i] = (uint8_t)best;
+            counts[x] = 0u;
+        }
+        if (threadIdx.x == 0) queue_n = 0;
+        __syncthreads();
+    }
+    // ---- the final records
+#pragma unroll
+    for (int s_ = 0; s_ < kEpQuads; ++s_) {
+        if (q_el[s_] >= 0) {
+            uint2* wp = reinterpret_cast<uint2*>(P.records + (((e0 + q_el[s_]) * N + i) * (int64_t)K + 4 * q_sq[s_]) * IA2C_BELIEF_RECORD);
+#pragma unroll
+            for (int w = 0; w < 4; ++w)
+                if (4 * q_sq[s_] + w < K) wp[w] = st[s_][w];
+        }
+    }
+}
+
+template <int M>
+int launch_pairs_episode(EpisodePairsArgs& P, cudaStream_t stream) {
+    const int KQ = (P.K + 3) / 4;
+    P.envs_per_block = std::max(1, (kEpQuads * kThreads) / KQ);   // <= kEpQuads quads per thread
+    const int64_t env_blocks = (P.E + P.envs_per_block - 1) / P.envs_per_block;
+    size_t smem = (104 + 3 * M * 101 + M * 3) * sizeof(double) + (((3 * M * 101 + 3) & ~3) + ((2 * M + 3) & ~3)) * sizeof(float) +
+                  (size_t)((P.envs_per_block + 3) & ~3) * sizeof(uint32_t) + kEpQueue * sizeof(uint4) +
+                  (size_t)2 * P.envs_per_block * KQ * sizeof(uint32_t);
+    smem = (smem + 15) & ~size_t(15);
+    dim3 grid((unsigned)env_blocks, P.N);
+    const bool fast = !P.u_injected && !P.belief_dump && !P.pred_dump;
+    if (fast) {
+        if (smem > 48 * 1024) cudaFuncSetAttribute(belief_pairs_episode_kernel<M, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        return launch_pdl("belief_pairs_episode_kernel", belief_pairs_episode_kernel<M, true>, grid, dim3(kThreads), smem, stream, P);
+    }
+    if (smem > 48 * 1024) cudaFuncSetAttribute(belief_pairs_episode_kernel<M, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    return launch_pdl("belief_pairs_episode_kernel", belief_pairs_episode_kernel<M, false>, grid, dim3(kThreads), smem, stream, P);
+}
+
 template <int M>
 int launch_pairs(PairsArgs& P, cudaStream_t stream) {
     if (P.K >= 32 && P.N <= 65535) return launch_pairs_table<M>(P, stream);
@@ -755,5 +1110,31 @@ extern "C" int ia2c_belief_update_pairs(uint8_t* records, const double* filter_a
         case 4: return launch_pairs<4>(P, s);
         case 5: return launch_pairs<5>(P, s);
         default: return launch_pairs<6>(P, s);
+    }
+}
+
+extern "C" int ia2c_belief_supports_episode(int32_t N, int32_t M) { return N >= 33 && N <= 1023 && (N & 3) == 0 && M >= 2 && M <= IA2C_MAX_MODELS; }
+
+extern "C" int ia2c_belief_update_pairs_episode(uint8_t* records, const double* filter_action, const uint8_t* act,
+                                                const double* u_injected, uint8_t* pred_dump, uint8_t* belief_dump,
+                                                uint8_t* partner_pred, int64_t E, int32_t N, int32_t M, int32_t T1, uint64_t seed,
+                                                uint32_t episode, int64_t env_offset, void* stream) {
+    IA2C_REQUIRE(E > 0 && T1 > 0 && records && filter_action && act && partner_pred, "ia2c_belief_update_pairs_episode: E=%lld T1=%d or null arrays",
+                 (long long)E, T1);
+    IA2C_REQUIRE(ia2c_belief_supports_episode(N, M), "ia2c_belief_update_pairs_episode: needs 33 <= N <= 1023, N %% 4 == 0, 2 <= M <= %d; got N=%d M=%d",
+                 IA2C_MAX_MODELS, N, M);
+    IA2C_REQUIRE(T1 <= 65535, "ia2c_belief_update_pairs_episode: T1=%d", T1);
+    EpisodePairsArgs P{records, filter_action, act, u_injected, pred_dump, belief_dump, partner_pred, E, env_offset, N, N - 1, T1, 0, episode, {}};
+    for (int r = 0; r < 10; ++r) {
+        P.rk[2 * r] = (uint32_t)seed + (uint32_t)r * 0x9E3779B9u;
+        P.rk[2 * r + 1] = (uint32_t)(seed >> 32) + (uint32_t)r * 0xBB67AE85u;
+    }
+    cudaStream_t s = as_stream(stream);
+    switch (M) {
+        case 2: return launch_pairs_episode<2>(P, s);
+        case 3: return launch_pairs_episode<3>(P, s);
+        case 4: return launch_pairs_episode<4>(P, s);
+        case 5: return launch_pairs_episode<5>(P, s);
+        default: return launch_pairs_episode<6>(P, s);
     }
 }

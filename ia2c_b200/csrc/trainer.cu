@@ -480,11 +480,16 @@ extern "C" int ia2c_rollout(const ia2c_episode_desc* d, void* stream) {
     const int64_t ept = std::max<int64_t>(1, std::min<int64_t>(kActorEnvsPerThread, d->E * d->N / ((int64_t)kActorThreads * 2 * kSMs)));
     dim3 actor_grid((unsigned)ceil_div(d->E, (int64_t)kActorThreads * ept), (unsigned)d->N);
     const int64_t EN = d->E * d->N, K = d->N - 1;
+    // Nothing reads a belief before the update phase (ia2c.py:72-102 vs :104-121), so with many modelled others the T+1 env /
+    // actor steps run first and ONE kernel then carries every belief record through the whole episode in registers
+    // (belief.cu: belief_pairs_episode_kernel) instead of streaming the records once per step.
+    const bool episode_beliefs = !(d->flags & IA2C_FLAG_BELIEF_PER_STEP) && ia2c_belief_supports_episode(d->N, d->M);
     for (int t = 0; t <= d->T + 1; ++t) {
         S.t = t;
         if (int rc = launch_pdl("env_step_kernel", env_step_kernel, dim3(blocks), dim3(kRolloutThreads), 0, s, S)) return rc;
         if (t > d->T) break;   // the last call only completes partner_true[T]
         if (int rc = launch_pdl("actor_step_kernel", actor_step_kernel, actor_grid, dim3(kActorThreads), 0, s, S)) return rc;
+        if (episode_beliefs) continue;
         int rc = ia2c_belief_update_pairs(
             d->belief_records, d->filter_action, d->act + (int64_t)t * EN,
             d->inj_u_belief ? d->inj_u_belief + (int64_t)t * EN * K : nullptr,
@@ -494,6 +499,9 @@ extern "C" int ia2c_rollout(const ia2c_episode_desc* d, void* stream) {
             (uint32_t)t, d->env_offset, stream);
         if (rc) return rc;
     }
+    if (episode_beliefs)
+        return ia2c_belief_update_pairs_episode(d->belief_records, d->filter_action, d->act, d->inj_u_belief, d->pred_dump, d->belief_dump,
+                                                d->partner_pred, d->E, d->N, d->M, d->T + 1, d->seed, d->episode, d->env_offset, stream);
     return 0;
 }
 

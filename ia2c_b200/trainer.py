@@ -50,7 +50,7 @@ class IA2CTrainer:
     def __init__(self, num_envs, n_agents=2, n_models=5, steps_per_episode=30, max_episode_steps=30,
                  lr_critic=0.0002, lr_actor=0.0001, beta=0.001, gamma=0.9, seed=0, device=None,
                  rank=0, world_size=1, process_group=None, dumps=False, fused_rollout=None, fused_critic=None,
-                 init=None, comm="auto", actor_kernel="auto"):
+                 init=None, comm="auto", actor_kernel="auto", belief_kernel="auto"):
         _lib.require_cuda()
         if actor_kernel not in ("auto", "pipe", "columns"):
             raise ValueError("actor_kernel must be 'auto', 'pipe' or 'columns'")
@@ -105,7 +105,12 @@ class IA2CTrainer:
             fused_rollout = bool(self.lib.ia2c_rollout_fused_supported(N, M))
         if fused_critic is None:
             fused_critic = bool(fused_rollout)   # the critic-gradient stage rides along with the fused rollout
+        if belief_kernel not in ("auto", "episode", "step"):
+            raise ValueError("belief_kernel must be 'auto', 'episode' or 'step'")
+        # many modelled others (N > 8 path): "auto" / "episode" carry every belief record through the whole episode in ONE
+        # kernel where the library supports it (N >= 33, N % 4 == 0), "step" streams the records once per step (A/B, parity)
         d.flags = ((_lib.FLAG_FUSED_ROLLOUT if fused_rollout else 0) | (_lib.FLAG_SKIP_ADAM if self.world > 1 else 0) |
+                   (_lib.FLAG_BELIEF_PER_STEP if belief_kernel == "step" else 0) |
                    (_lib.FLAG_FUSED_CRITIC if (fused_rollout and fused_critic) else 0) |
                    (_lib.FLAG_ACTOR_COLUMNS if actor_kernel == "columns" else 0))
         for name in ("actor_params", "actor_grad", "actor_grad_accum", "actor_m", "actor_v", "critic_params",

@@ -101,6 +101,17 @@ int ia2c_belief_update_pairs(uint8_t* records, const double* filter_action, cons
                              uint8_t* pred_partner_out, int64_t E, int32_t N, int32_t M, int32_t reset_prior,
                              uint64_t seed, uint32_t episode, uint32_t t, int64_t env_offset, void* stream);
 
+/* The same update carried through a WHOLE episode in one launch (the trainer's rollout for many modelled others): the record
+ * lives in registers from the uniform prior of step 0 (ia2c.py:79) to step T1-1 and is written once; the per-step inputs
+ * and outputs are the trajectory arrays.  Bit-identical to T1 calls of ia2c_belief_update_pairs (reset_prior at the first).
+ *   act uint8[T1,E,N]; u_injected double[T1,E,N,K] or NULL -> Philox(seed, episode, t, ...);
+ *   pred_dump uint8[T1,E,N,K], belief_dump uint8[T1,E,N,K,M] (may be NULL); partner_pred uint8[T1,E,N] out;
+ *   records uint8[E,N,K,8] out.  Requires ia2c_belief_supports_episode(N, M): 33 <= N <= 1023, N % 4 == 0. */
+int ia2c_belief_supports_episode(int32_t N, int32_t M);
+int ia2c_belief_update_pairs_episode(uint8_t* records, const double* filter_action, const uint8_t* act, const double* u_injected,
+                                     uint8_t* pred_dump, uint8_t* belief_dump, uint8_t* partner_pred, int64_t E, int32_t N,
+                                     int32_t M, int32_t T1, uint64_t seed, uint32_t episode, int64_t env_offset, void* stream);
+
 /* Diagnostic: q_seq[i] = the library's branch-free fp64 division sequence (csrc/common.cuh: ddiv_seq),
  * q_ieee[i] = IEEE a/b (__ddiv_rn).  Used by the tests to prove the two agree bit for bit on the
  * operand ranges the belief filter and the reward recurrence produce. */
@@ -250,6 +261,8 @@ typedef struct ia2c_episode_desc {
                                        ia2c_allreduce_adam then reduces, exchanges and steps */
 #define IA2C_FLAG_ACTOR_COLUMNS 16  /* actor phase: use the time-chunk column kernel instead of the pipelined one (A/B, parity tests) */
 #define IA2C_FLAG_SKIP_ADAM     2   /* stop after writing gradients (multi-GPU: all-reduce, then ia2c_adam_step) */
+#define IA2C_FLAG_BELIEF_PER_STEP 32 /* rollout (N > 8): one belief kernel per step (ia2c_belief_update_pairs) instead of the
+                                      * whole-episode kernel (ia2c_belief_update_pairs_episode) — A/B and parity tests */
 
 size_t ia2c_episode_partials_floats(const ia2c_episode_desc* d);
 

@@ -148,3 +148,37 @@ def test_pairs_fast_path_vs_oracle_at_scale():
         assert np.array_equal(r[..., :M], B.to_hundredths(obp)) and np.array_equal(r[..., 6], oap) and not r[..., 7].any()
         assert np.array_equal(host(partner), mode3(oap))
         prior = obp
+
+
+@pytest.mark.parametrize("E,N,M,T1,injected", [(5, 36, 5, 6, True), (40, 64, 5, 5, False), (3, 132, 5, 4, True), (17, 256, 5, 4, False),
+                                               (70, 36, 3, 5, False), (2, 1020, 5, 2, False)])
+def test_episode_kernel_equals_the_per_step_kernel(E, N, M, T1, injected):
+    """ia2c_belief_update_pairs_episode (records resident in registers for the whole episode) against T1 calls of the per-step
+    kernel, which the oracle tests above pin: records, per-step predictions, per-step posteriors and partner modes, byte for byte."""
+    import torch
+    from ia2c_b200 import _lib
+    lib = _lib.load()
+    assert lib.ia2c_belief_supports_episode(N, M) == 1 and lib.ia2c_belief_supports_episode(130, 5) == 0
+    rng = np.random.RandomState(E * 7 + N)
+    K = N - 1
+    fa = rng.rand(N, M, 3)
+    fa /= fa.sum(-1, keepdims=True)
+    fa_d = dev(fa)
+    act = dev(rng.randint(0, 3, size=(T1, E, N)).astype(np.uint8))
+    u = dev(rng.rand(T1, E, N, K)) if injected else None
+    z = lambda *shape: torch.zeros(*shape, dtype=torch.uint8, device="cuda")
+    rec_s, pred_s, bel_s, part_s = z(E, N, K, 8), z(T1, E, N, K), z(T1, E, N, K, M), z(T1, E, N)
+    for t in range(T1):
+        _lib.check(lib.ia2c_belief_update_pairs(_lib.ptr(rec_s), _lib.ptr(fa_d), _lib.ptr(act[t]), _lib.ptr(u[t]) if injected else None,
+                                                _lib.ptr(pred_s[t]), _lib.ptr(bel_s[t]), _lib.ptr(part_s[t]), E, N, M, int(t == 0), 21, 4, t, 100,
+                                                _lib.stream_ptr()))
+    rec_e, pred_e, bel_e, part_e = z(E, N, K, 8) + 7, z(T1, E, N, K), z(T1, E, N, K, M), z(T1, E, N)
+    _lib.check(lib.ia2c_belief_update_pairs_episode(_lib.ptr(rec_e), _lib.ptr(fa_d), _lib.ptr(act), _lib.ptr(u) if injected else None,
+                                                    _lib.ptr(pred_e), _lib.ptr(bel_e), _lib.ptr(part_e), E, N, M, T1, 21, 4, 100, _lib.stream_ptr()))
+    assert torch.equal(part_e, part_s) and torch.equal(pred_e, pred_s) and torch.equal(bel_e, bel_s) and torch.equal(rec_e, rec_s)
+    # the steady-state template (no dumps) writes the same records and partner modes
+    rec_f, part_f = z(E, N, K, 8), z(T1, E, N)
+    if not injected:
+        _lib.check(lib.ia2c_belief_update_pairs_episode(_lib.ptr(rec_f), _lib.ptr(fa_d), _lib.ptr(act), None, None, None, _lib.ptr(part_f), E, N, M, T1,
+                                                        21, 4, 100, _lib.stream_ptr()))
+        assert torch.equal(rec_f, rec_s) and torch.equal(part_f, part_s)
