@@ -710,7 +710,6 @@ struct EpisodePairsArgs {
     uint32_t rk[20];
 };
 constexpr int kEpQuads = 4;        // quads per thread
-constexpr int kEpQueue = 512;      // deferred records per block and step
 
 template <int M, bool FAST>
 __global__ void __launch_bounds__(kThreads, 2) belief_pairs_episode_kernel(const __grid_constant__ EpisodePairsArgs P) {
@@ -732,8 +731,9 @@ __global__ void __launch_bounds__(kThreads, 2) belief_pairs_episode_kernel(const
     float* bpt32 = reinterpret_cast<float*>(fa + M * A);             // [A][M][101]
     float* fcum = bpt32 + ((A * M * 101 + 3) & ~3);                  // [2][M]: F[m][0], F[m][0]+F[m][1]
     uint32_t* counts = reinterpret_cast<uint32_t*>(fcum + ((2 * M + 3) & ~3));   // [EC] packed 3 x 10 bits
-    uint4* queue = reinterpret_cast<uint4*>(counts + ((EC + 3) & ~3));           // [kEpQueue] {raw.x, raw.y, word or u index, seen | result}
-    uint32_t* seen4 = reinterpret_cast<uint32_t*>(queue + kEpQueue);              // [2][EC][KQ] the others' actions, double-buffered
+    uint2* st_mem = reinterpret_cast<uint2*>(counts + ((EC + 3) & ~3));          // [4 * kEpQuads][kThreads] the records of the block
+    uint16_t* queue = reinterpret_cast<uint16_t*>(st_mem + 4 * kEpQuads * kThreads);   // [4 * kEpQuads * kThreads] flagged records (cannot overflow)
+    uint32_t* seen4 = reinterpret_cast<uint32_t*>(queue + 4 * kEpQuads * kThreads);     // [2][EC][KQ] the others' actions, double-buffered
     pdl_release();
     for (int k = threadIdx.x; k <= 100; k += blockDim.x) tab[k] = __ddiv_rn((double)k, 100.0);
     for (int k = threadIdx.x; k < M * A; k += blockDim.x) fa[k] = P.filter_action[(int64_t)i * M * A + k];
@@ -815,23 +815,20 @@ __global__ void __launch_bounds__(kThreads, 2) belief_pairs_episode_kernel(const
         return (exA ? 1u : 0u) | (exB ? 2u : 0u);
     };
 
-    // ---- the thread's quads (fixed for the whole episode) and their state
+    // ---- the thread's quads (fixed for the whole episode): quad q = tid + s * 256, s < kEpQuads.  The records live in shared memory
+    // ([slot][thread] 8-byte words: conflict-free), so the quad loop is a real loop (the step body stays inside the instruction
+    // cache) and the exact pass can fix a flagged record in place.
     const int total = n_envs * KQ;
     const bool warp_one_env = (KQ & 31) == 0;
     const int prior_k = (int)rint(100.0 / M);
     uint2 prior;
     prior.x = (uint32_t)prior_k * (M >= 4 ? 0x01010101u : (M == 3 ? 0x010101u : 0x0101u));
     prior.y = M > 4 ? (uint32_t)prior_k * (M > 5 ? 0x0101u : 0x01u) : 0u;
-    int q_el[kEpQuads], q_sq[kEpQuads];
-    uint2 st[kEpQuads][4];
+    const uint32_t st_s = (uint32_t)__cvta_generic_to_shared(st_mem) + threadIdx.x * 8u;   // + (4 s + w) * kThreads * 8
 #pragma unroll
-    for (int s_ = 0; s_ < kEpQuads; ++s_) {
-        const int q = (int)threadIdx.x + s_ * (int)blockDim.x;
-        q_el[s_] = q < total ? q / KQ : -1;
-        q_sq[s_] = q < total ? q % KQ : 0;
-#pragma unroll
-        for (int w = 0; w < 4; ++w) st[s_][w] = prior;
-    }
+    for (int k = 0; k < 4 * kEpQuads; ++k) st_mem[k * kThreads + threadIdx.x] = prior;
+    const int d_el = (int)blockDim.x / KQ, d_sq = (int)blockDim.x % KQ;
+    const int el0 = (int)threadIdx.x / KQ, sq0 = (int)threadIdx.x % KQ;
     const uint64_t ctr0 = (uint64_t)((P.env_offset + e0) * N + i) * (uint64_t)KQ;
     const uint32_t row_ctr = (uint32_t)N * (uint32_t)KQ;
     // staging of the others' actions of one step (own action skipped, 4 slots per word); requires N % 4 == 0 (checked by the host)
@@ -840,23 +837,35 @@ __global__ void __launch_bounds__(kThreads, 2) belief_pairs_episode_kernel(const
     uint32_t stage_lo[kEpQuads], stage_hi[kEpQuads];
     auto stage_load = [&](int t) {
         const uint32_t* src = reinterpret_cast<const uint32_t*>(P.act + ((int64_t)t * P.E + e0) * N);
+        int el = el0, sq = sq0;
 #pragma unroll
         for (int s_ = 0; s_ < kEpQuads; ++s_) {
-            const bool ok = q_el[s_] >= 0;
-            stage_lo[s_] = ok ? __ldg(src + q_el[s_] * NW + q_sq[s_]) : 0u;
-            stage_hi[s_] = (ok && q_sq[s_] + 1 < NW) ? __ldg(src + q_el[s_] * NW + q_sq[s_] + 1) : 0u;
+            const bool ok = (int)threadIdx.x + s_ * (int)blockDim.x < total;
+            stage_lo[s_] = ok ? __ldg(src + el * NW + sq) : 0u;
+            stage_hi[s_] = (ok && sq + 1 < NW) ? __ldg(src + el * NW + sq + 1) : 0u;
+            el += d_el; sq += d_sq;
+            if (sq >= KQ) { sq -= KQ; ++el; }
         }
     };
     auto stage_store = [&](int buf) {
+        int el = el0, sq = sq0;
 #pragma unroll
         for (int s_ = 0; s_ < kEpQuads; ++s_) {
-            if (q_el[s_] >= 0) {
-                const int w = q_sq[s_];
-                uint32_t v = __byte_perm(stage_lo[s_], stage_hi[s_], w < iw ? 0x3210u : (w > iw ? 0x4321u : sel_mix));
-                if (4 * w + 3 >= K) v &= 0xFFFFFFFFu >> (8 * (4 * w + 4 - K));
-                seen4[buf * (EC * KQ) + q_el[s_] * KQ + w] = v;
+            if ((int)threadIdx.x + s_ * (int)blockDim.x < total) {
+                uint32_t v = __byte_perm(stage_lo[s_], stage_hi[s_], sq < iw ? 0x3210u : (sq > iw ? 0x4321u : sel_mix));
+                if (4 * sq + 3 >= K) v &= 0xFFFFFFFFu >> (8 * (4 * sq + 4 - K));
+                seen4[buf * (EC * KQ) + el * KQ + sq] = v;
             }
+            el += d_el; sq += d_sq;
+            if (sq >= KQ) { sq -= KQ; ++el; }
         }
+    };
+    auto dump = [&](int64_t trec, uint2 out) {
+        if (belief_dump) {
+#pragma unroll
+            for (int m = 0; m < M; ++m) belief_dump[trec * M + m] = (uint8_t)(((m < 4 ? out.x : out.y) >> (8 * (m & 3))) & 0xFFu);
+        }
+        if (pred_dump) pred_dump[trec] = (uint8_t)(out.y >> 16);
     };
     stage_load(0);
     stage_store(0);
@@ -867,22 +876,28 @@ __global__ void __launch_bounds__(kThreads, 2) belief_pairs_episode_kernel(const
         const int buf = t & 1;
         if (t + 1 < P.T1) stage_load(t + 1);                       // next step's actions: in flight during this step's arithmetic
         const uint32_t c2 = ((uint32_t)t & 0xFFFFu) | (kStreamBelief << 16);
-        uint32_t need16 = 0u;
-#pragma unroll
+        const int64_t tbase = (int64_t)t * P.E * N * K;            // index of step t in the per-step tapes / dumps
+        int el = el0, sq = sq0;
+#pragma unroll 1
         for (int s_ = 0; s_ < kEpQuads; ++s_) {
-            const int el = q_el[s_], sq = q_sq[s_];
-            const bool live = el >= 0;
+            const int q = (int)threadIdx.x + s_ * (int)blockDim.x;
+            if (q - lane >= total) break;                          // warp-uniform: whole warp past the end
+            const bool live = q < total;
             const int jj0 = 4 * sq;
             const int n_valid = live ? min(4, K - jj0) : 0;
-            const int64_t rec0 = ((e0 + (live ? el : 0)) * N + i) * (int64_t)K + jj0;
-            const int64_t trec0 = (int64_t)t * P.E * N * K + rec0;      // index into the per-step tapes / dumps
+            const int64_t trec0 = tbase + ((e0 + (live ? el : 0)) * N + i) * (int64_t)K + jj0;
             uint32_t words[4] = {0u, 0u, 0u, 0u};
             if (!u_injected) {
                 const uint64_t index = ctr0 + (uint32_t)(live ? el : 0) * row_ctr + (uint32_t)sq;
                 const uint4 rnd = philox4x32_10_rk(make_uint4((uint32_t)index, (uint32_t)(index >> 32), c2, P.episode), P.rk);
                 words[0] = rnd.x; words[1] = rnd.y; words[2] = rnd.z; words[3] = rnd.w;
             }
-            const uint32_t seen_w = live ? seen4[buf * (EC * KQ) + el * KQ + sq] : 0u;
+            const uint32_t seen_w = live ? seen4[buf * (EC * KQ) + q] : 0u;
+            const uint32_t sp = st_s + (uint32_t)(4 * s_) * (kThreads * 8u);
+            uint2 raw[4];
+#pragma unroll
+            for (int w = 0; w < 4; ++w)
+                asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(raw[w].x), "=r"(raw[w].y) : "r"(sp + (kThreads * 8u) * w) : "memory");
             float uf[4];
 #pragma unroll
             for (int w = 0; w < 4; ++w) {
@@ -890,106 +905,57 @@ __global__ void __launch_bounds__(kThreads, 2) belief_pairs_episode_kernel(const
                 else uf[w] = __uint_as_float(0x3F800000u | (words[w] >> 9)) - 1.0f;
             }
             uint2 out[4];
-            uint32_t need = screen_pair(__byte_perm(seen_w, 0u, 0x4440u), __byte_perm(seen_w, 0u, 0x4441u), uf[0], uf[1], st[s_][0], st[s_][1], out[0], out[1]);
-            need |= screen_pair(__byte_perm(seen_w, 0u, 0x4442u), __byte_perm(seen_w, 0u, 0x4443u), uf[2], uf[3], st[s_][2], st[s_][3], out[2], out[3]) << 2;
+            uint32_t need = screen_pair(__byte_perm(seen_w, 0u, 0x4440u), __byte_perm(seen_w, 0u, 0x4441u), uf[0], uf[1], raw[0], raw[1], out[0], out[1]);
+            need |= screen_pair(__byte_perm(seen_w, 0u, 0x4442u), __byte_perm(seen_w, 0u, 0x4443u), uf[2], uf[3], raw[2], raw[3], out[2], out[3]) << 2;
             need &= (1u << n_valid) - 1u;
             uint32_t packed = 0u;
 #pragma unroll
             for (int w = 0; w < 4; ++w) {
                 if (w < n_valid && !(need & (1u << w))) {
-                    st[s_][w] = out[w];
+                    asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(sp + (kThreads * 8u) * w), "r"(out[w].x), "r"(out[w].y) : "memory");
                     packed += 1u << (10u * (out[w].y >> 16));
-                    if (belief_dump) {
-#pragma unroll
-                        for (int m = 0; m < M; ++m) belief_dump[(trec0 + w) * M + m] = (uint8_t)(((m < 4 ? out[w].x : out[w].y) >> (8 * (m & 3))) & 0xFFu);
-                    }
-                    if (pred_dump) pred_dump[trec0 + w] = (uint8_t)(out[w].y >> 16);
+                    if (belief_dump || pred_dump) dump(trec0 + w, out[w]);
                 }
             }
-            need16 |= need << (4 * s_);
+            if (need) {   // ~1 % of the quads: the flagged records go to the dense exact pass below, which fixes them in place
+                int pos = atomicAdd(&queue_n, __popc(need));
+#pragma unroll
+                for (int w = 0; w < 4; ++w)
+                    if (need & (1u << w)) queue[pos++] = (uint16_t)((q << 2) | w);
+            }
             if (warp_one_env) {
                 const uint32_t sum = __reduce_add_sync(0xffffffffu, packed);
-                if (lane == 0 && live) atomicAdd(&counts[el], sum);
+                if (lane == 0) atomicAdd(&counts[el], sum);
             } else {
-                const unsigned peers = __match_any_sync(0xffffffffu, el);
+                const unsigned peers = __match_any_sync(__activemask(), live ? el : -1);
                 const uint32_t sum = __reduce_add_sync(peers, packed);
                 if (lane == __ffs(peers) - 1 && live) atomicAdd(&counts[el], sum);
             }
-        }
-        // ---- deferred exact pass: flagged records -> queue -> dense fp64 sequence -> owners patch their registers
-        int qbase = 0;
-        if (need16) {
-            qbase = atomicAdd(&queue_n, __popc(need16));
-            int pos = qbase;
-#pragma unroll
-            for (int s_ = 0; s_ < kEpQuads; ++s_) {
-#pragma unroll
-                for (int w = 0; w < 4; ++w) {
-                    if (need16 & (1u << (4 * s_ + w))) {
-                        const uint32_t seen = (seen4[buf * (EC * KQ) + q_el[s_] * KQ + q_sq[s_]] >> (8 * w)) & 0xFFu;
-                        const uint32_t code = ((uint32_t)(q_el[s_] * KQ + q_sq[s_]) << 2) | (uint32_t)w;   // quad << 2 | slot
-                        if (pos < kEpQueue) queue[pos] = make_uint4(st[s_][w].x, st[s_][w].y, code, seen);
-                        ++pos;
-                    }
-                }
-            }
+            el += d_el; sq += d_sq;
+            if (sq >= KQ) { sq -= KQ; ++el; }
         }
         __syncthreads();
-        const int n_def = min(queue_n, kEpQueue);
+        // ---- exact pass: the flagged records, one per thread, with the reference's fp64 sequence, fixed in place
+        const int n_def = queue_n;
         for (int x = threadIdx.x; x < n_def; x += blockDim.x) {
-            const uint4 en = queue[x];
-            const int q = (int)(en.z >> 2), w = (int)(en.z & 3u);
+            const int code = queue[x], q = code >> 2, w = code & 3;
             const int el_ = q / KQ, sq_ = q - el_ * KQ;
+            const int owner = q % (int)blockDim.x, s_ = q / (int)blockDim.x;
+            uint2* rp = st_mem + (4 * s_ + w) * kThreads + owner;
+            const int64_t trec = tbase + ((e0 + el_) * N + i) * (int64_t)K + 4 * sq_ + w;
             double u;
             if (u_injected) {
-                u = u_injected[(int64_t)t * P.E * N * K + ((e0 + el_) * N + i) * (int64_t)K + 4 * sq_ + w];
+                u = u_injected[trec];
             } else {
                 const uint64_t index = ctr0 + (uint32_t)el_ * row_ctr + (uint32_t)sq_;
                 const uint4 rnd = philox4x32_10_rk(make_uint4((uint32_t)index, (uint32_t)(index >> 32), c2, P.episode), P.rk);
                 u = belief_word_to_unit_f64(w == 0 ? rnd.x : (w == 1 ? rnd.y : (w == 2 ? rnd.z : rnd.w)));
             }
-            const uint2 res = belief_exact_record<M>(bpt + en.w * (M * 101), fa, make_uint2(en.x, en.y), -1, u);
-            queue[x] = make_uint4(res.x, res.y, en.z, en.w);
-        }
-        __syncthreads();
-        if (need16) {
-            int pos = qbase;
-#pragma unroll
-            for (int s_ = 0; s_ < kEpQuads; ++s_) {
-#pragma unroll
-                for (int w = 0; w < 4; ++w) {
-                    if (need16 & (1u << (4 * s_ + w))) {
-                        uint2 res;
-                        if (pos < kEpQueue) {
-                            const uint4 en = queue[pos];
-                            res = make_uint2(en.x, en.y);
-                        } else {   // queue full (never seen in practice): the exact sequence right here
-                            const uint32_t seen = (seen4[buf * (EC * KQ) + q_el[s_] * KQ + q_sq[s_]] >> (8 * w)) & 0xFFu;
-                            const int64_t trec = (int64_t)t * P.E * N * K + ((e0 + q_el[s_]) * N + i) * (int64_t)K + 4 * q_sq[s_] + w;
-                            double u;
-                            if (u_injected) {
-                                u = u_injected[trec];
-                            } else {
-                                const uint64_t index = ctr0 + (uint32_t)q_el[s_] * row_ctr + (uint32_t)q_sq[s_];
-                                const uint4 rnd = philox4x32_10_rk(make_uint4((uint32_t)index, (uint32_t)(index >> 32), c2, P.episode), P.rk);
-                                u = belief_word_to_unit_f64(w == 0 ? rnd.x : (w == 1 ? rnd.y : (w == 2 ? rnd.z : rnd.w)));
-                            }
-                            res = belief_exact_record<M>(bpt + seen * (M * 101), fa, st[s_][w], -1, u);
-                        }
-                        ++pos;
-                        st[s_][w] = res;
-                        atomicAdd(&counts[q_el[s_]], 1u << (10u * (res.y >> 16)));
-                        if (belief_dump || pred_dump) {
-                            const int64_t trec = (int64_t)t * P.E * N * K + ((e0 + q_el[s_]) * N + i) * (int64_t)K + 4 * q_sq[s_] + w;
-                            if (belief_dump) {
-#pragma unroll
-                                for (int m = 0; m < M; ++m) belief_dump[trec * M + m] = (uint8_t)(((m < 4 ? res.x : res.y) >> (8 * (m & 3))) & 0xFFu);
-                            }
-                            if (pred_dump) pred_dump[trec] = (uint8_t)(res.y >> 16);
-                        }
-                    }
-                }
-            }
+            const uint32_t seen = (seen4[buf * (EC * KQ) + q] >> (8 * w)) & 0xFFu;
+            const uint2 res = belief_exact_record<M>(bpt + seen * (M * 101), fa, *rp, -1, u);
+            *rp = res;
+            atomicAdd(&counts[el_], 1u << (10u * (res.y >> 16)));
+            if (belief_dump || pred_dump) dump(trec, res);
         }
         if (t + 1 < P.T1) stage_store(buf ^ 1);                    // nobody reads that buffer during this step
         __syncthreads();
@@ -1007,13 +973,18 @@ __global__ void __launch_bounds__(kThreads, 2) belief_pairs_episode_kernel(const
         __syncthreads();
     }
     // ---- the final records
+    {
+        int el = el0, sq = sq0;
 #pragma unroll
-    for (int s_ = 0; s_ < kEpQuads; ++s_) {
-        if (q_el[s_] >= 0) {
-            uint2* wp = reinterpret_cast<uint2*>(P.records + (((e0 + q_el[s_]) * N + i) * (int64_t)K + 4 * q_sq[s_]) * IA2C_BELIEF_RECORD);
+        for (int s_ = 0; s_ < kEpQuads; ++s_) {
+            if ((int)threadIdx.x + s_ * (int)blockDim.x < total) {
+                uint2* wp = reinterpret_cast<uint2*>(P.records + (((e0 + el) * N + i) * (int64_t)K + 4 * sq) * IA2C_BELIEF_RECORD);
 #pragma unroll
-            for (int w = 0; w < 4; ++w)
-                if (4 * q_sq[s_] + w < K) wp[w] = st[s_][w];
+                for (int w = 0; w < 4; ++w)
+                    if (4 * sq + w < K) wp[w] = st_mem[(4 * s_ + w) * kThreads + threadIdx.x];
+            }
+            el += d_el; sq += d_sq;
+            if (sq >= KQ) { sq -= KQ; ++el; }
         }
     }
 }
@@ -1024,7 +995,7 @@ int launch_pairs_episode(EpisodePairsArgs& P, cudaStream_t stream) {
     P.envs_per_block = std::max(1, (kEpQuads * kThreads) / KQ);   // <= kEpQuads quads per thread
     const int64_t env_blocks = (P.E + P.envs_per_block - 1) / P.envs_per_block;
     size_t smem = (104 + 3 * M * 101 + M * 3) * sizeof(double) + (((3 * M * 101 + 3) & ~3) + ((2 * M + 3) & ~3)) * sizeof(float) +
-                  (size_t)((P.envs_per_block + 3) & ~3) * sizeof(uint32_t) + kEpQueue * sizeof(uint4) +
+                  (size_t)((P.envs_per_block + 3) & ~3) * sizeof(uint32_t) + (size_t)4 * kEpQuads * kThreads * (sizeof(uint2) + sizeof(uint16_t)) +
                   (size_t)2 * P.envs_per_block * KQ * sizeof(uint32_t);
     smem = (smem + 15) & ~size_t(15);
     dim3 grid((unsigned)env_blocks, P.N);
