@@ -834,30 +834,34 @@ __global__ void __launch_bounds__(kThreads, 2) belief_pairs_episode_kernel(const
     // staging of the others' actions of one step (own action skipped, 4 slots per word); requires N % 4 == 0 (checked by the host)
     const int NW = N >> 2, iw = i >> 2;
     const uint32_t sel_mix = (i & 3) == 0 ? 0x4321u : ((i & 3) == 1 ? 0x4320u : ((i & 3) == 2 ? 0x4310u : 0x4210u));
-    uint32_t stage_lo[kEpQuads], stage_hi[kEpQuads];
-    auto stage_load = [&](int t) {
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(P.act + ((int64_t)t * P.E + e0) * N);
+    // per quad, fixed for the episode: source word offset, byte selector, destination word.  Padding slots (jj >= K) keep
+    // whatever action byte the selector picks — they are computed on but never stored or counted.
+    uint32_t stage_lo[kEpQuads], stage_hi[kEpQuads], stage_src[kEpQuads], stage_sel[kEpQuads];
+    {
         int el = el0, sq = sq0;
 #pragma unroll
         for (int s_ = 0; s_ < kEpQuads; ++s_) {
             const bool ok = (int)threadIdx.x + s_ * (int)blockDim.x < total;
-            stage_lo[s_] = ok ? __ldg(src + el * NW + sq) : 0u;
-            stage_hi[s_] = (ok && sq + 1 < NW) ? __ldg(src + el * NW + sq + 1) : 0u;
+            stage_src[s_] = ok ? (uint32_t)(el * NW + sq) : 0xFFFFFFFFu;
+            stage_sel[s_] = (sq < iw ? 0x3210u : (sq > iw ? 0x4321u : sel_mix)) | (sq + 1 < NW ? 0u : 0x80000000u);   // bit 31: no next word
             el += d_el; sq += d_sq;
             if (sq >= KQ) { sq -= KQ; ++el; }
         }
-    };
-    auto stage_store = [&](int buf) {
-        int el = el0, sq = sq0;
+    }
+    auto stage_load = [&](int t) {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(P.act + ((int64_t)t * P.E + e0) * N);
 #pragma unroll
         for (int s_ = 0; s_ < kEpQuads; ++s_) {
-            if ((int)threadIdx.x + s_ * (int)blockDim.x < total) {
-                uint32_t v = __byte_perm(stage_lo[s_], stage_hi[s_], sq < iw ? 0x3210u : (sq > iw ? 0x4321u : sel_mix));
-                if (4 * sq + 3 >= K) v &= 0xFFFFFFFFu >> (8 * (4 * sq + 4 - K));
-                seen4[buf * (EC * KQ) + el * KQ + sq] = v;
-            }
-            el += d_el; sq += d_sq;
-            if (sq >= KQ) { sq -= KQ; ++el; }
+            const bool ok = stage_src[s_] != 0xFFFFFFFFu;
+            stage_lo[s_] = ok ? __ldg(src + stage_src[s_]) : 0u;
+            stage_hi[s_] = (ok && !(stage_sel[s_] >> 31)) ? __ldg(src + stage_src[s_] + 1) : 0u;
+        }
+    };
+    auto stage_store = [&](int buf) {
+#pragma unroll
+        for (int s_ = 0; s_ < kEpQuads; ++s_) {
+            const int q = (int)threadIdx.x + s_ * (int)blockDim.x;
+            if (q < total) seen4[buf * (EC * KQ) + q] = __byte_perm(stage_lo[s_], stage_hi[s_], stage_sel[s_] & 0xFFFFu);
         }
     };
     auto dump = [&](int64_t trec, uint2 out) {
