@@ -437,7 +437,7 @@ def parity_check(ctx, comm):
     import numpy as np
     torch = ctx.torch
     ok, max_rel, cases = True, 0.0, []
-    for N, E_total, fused in ((2, 64 * ctx.world, True), (66, 2 * ctx.world, False)):
+    for N, E_total, fused in ((2, 64 * ctx.world, True), (66, 2 * ctx.world, False), (68, 2 * ctx.world, False)):
         sharded = make_trainer(ctx, E_total, N, fused=fused, comm=comm, seed=11, dumps=True)
         single_ctx_world, single_ctx_rank = ctx.world, ctx.rank
         from ia2c_b200.trainer import IA2CTrainer, reference_init
@@ -663,43 +663,59 @@ def bench_org_n(ctx, args, _lib, name, label, E_total, N, steps, warmup, peak_gb
     launches = _lib.launch_count() - l0
     ms = ctx.max_over_ranks(total) / steps
     tr.check_comm()
-    # dominant kernel: the pairwise belief update (31 launches per episode) on the trainer's own records, same shape
+    # dominant kernel: the belief update of the episode's T+1 steps on the trainer's own buffers, same shape, timed standalone
     E, K = tr.E, N - 1
     st = _lib.stream_ptr()
-
-    def belief():
-        _lib.check(lib.ia2c_belief_update_pairs(_lib.ptr(tr.belief_records), _lib.ptr(tr.filter_action), _lib.ptr(tr.act[1]), None, None, None,
-                                                _lib.ptr(tr.partner_pred[1]), E, N, N_MODELS, 0, 5, 0, 1, tr.env_offset, st))
+    T1 = T_STEPS + 1
+    episode_kernel = bool(lib.ia2c_belief_supports_episode(N, N_MODELS)) and not (tr.desc.flags & _lib.FLAG_BELIEF_PER_STEP)
+    if episode_kernel:
+        def belief():
+            _lib.check(lib.ia2c_belief_update_pairs_episode(_lib.ptr(tr.belief_records), _lib.ptr(tr.filter_action), _lib.ptr(tr.act), None, None,
+                                                            None, _lib.ptr(tr.partner_pred), E, N, N_MODELS, T1, 5, 0, tr.env_offset, st))
+        launches_per_episode = 1
+    else:
+        def belief():
+            _lib.check(lib.ia2c_belief_update_pairs(_lib.ptr(tr.belief_records), _lib.ptr(tr.filter_action), _lib.ptr(tr.act[1]), None, None, None,
+                                                    _lib.ptr(tr.partner_pred[1]), E, N, N_MODELS, 0, 5, 0, 1, tr.env_offset, st))
+        launches_per_episode = T1
     for _ in range(2):
         belief()
-    n_b = 6
+    n_b = 3 if episode_kernel else 6
     bs, be = ctx.ev(), ctx.ev()
-    if small:
-        tot = 0.0
-        for _ in range(n_b):
+    tot = 0.0
+    for _ in range(n_b):
+        if small:
             ctx.flush()
-            bs.record(); belief(); be.record(); be.synchronize()
-            tot += bs.elapsed_time(be)
-        b_us = tot / n_b * 1e3
-    else:
-        bs.record()
-        for _ in range(n_b):
-            belief()
-        be.record(); be.synchronize()
-        b_us = bs.elapsed_time(be) / n_b * 1e3
+        bs.record(); belief(); be.record(); be.synchronize()
+        tot += bs.elapsed_time(be)
+    b_us = tot / n_b * 1e3
     pairs = E * N * K
-    achieved = 16 * pairs / (b_us * 1e-6) / 1e9
+    updates = pairs * (T1 if episode_kernel else 1)
+    # actual unique bytes: the episode kernel writes each 8-byte record ONCE per episode and reads one action byte per update
+    # (+ the partner mode per (env, agent, step)); the per-step kernel reads and writes the record at every update
+    bytes_per_launch = (8 * pairs + updates + E * N * T1) if episode_kernel else 16 * pairs
+    achieved = bytes_per_launch / (b_us * 1e-6) / 1e9
     units = E_total * N * T_STEPS
     value = units / (ms * 1e-3)
+    roof = {"kernel": ("belief_pairs_episode_kernel<5>" if episode_kernel else ("belief_pairs_table_kernel<5>" if K >= 32 else "belief_pairs_kernel<5>")),
+            "bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs, "traffic": bytes_per_launch,
+            "bytes_per_launch": bytes_per_launch, "us_per_launch": b_us, "launches_per_episode": launches_per_episode,
+            "share_of_step": launches_per_episode * b_us * 1e-3 / ms, "updates_per_s": updates / (b_us * 1e-6)}
+    if episode_kernel:
+        roof["streaming_equivalent"] = {"bytes_per_update": 16, "achieved": 16 * updates / (b_us * 1e-6) / 1e9,
+                                        "frac": 16 * updates / (b_us * 1e-6) / 1e9 / peak_gbs}
+        roof["note"] = ("the record stays in registers / shared memory for all T+1 updates of an episode and is written once, so the kernel "
+                        "no longer streams: ~1.3 B of unique traffic per update instead of the 16 B (8-byte record read + written) of the per-step "
+                        "kernel — it is bound by instruction issue on the ALU pipe (116 instructions per update, issue slots 61 %: "
+                        "profiles/r02_ncu_summary.md). 'streaming_equivalent' is the HBM rate the per-step kernel (kernels[]: 0.42 of peak standalone) "
+                        "would need for the same updates/s")
+    else:
+        roof["note"] = ("16 B per (agent, modelled-other) update: 8-byte record read + written (uint8-hundredths layout, lossless; the reference "
+                        "layout would be 88 B); ncu dram traffic = the algorithmic 16 B/record (profiles/)")
     out = {"config": name, "workload": label, "envs_total": E_total, "envs_per_gpu": E, "agents": N, "n_gpus": ctx.world, "scaling": scaling,
            "steps": steps, "warmup": warmup, "ms_per_step": ms, "value": value, "unit": UNIT, "gpu_launches": int(launches), "comm": tr.comm,
-           "l2": "L2 flushed between steps" if small else "per-step working set (belief records) larger than L2",
-           "roofline": {"kernel": "belief_pairs_table_kernel<5>" if K >= 32 else "belief_pairs_kernel<5>", "bound": "hbm", "achieved": achieved,
-                        "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs, "traffic": 16 * pairs, "bytes_per_launch": 16 * pairs,
-                        "us_per_launch": b_us, "share_of_step": (T_STEPS + 1) * b_us * 1e-3 / ms,
-                        "note": "16 B per (agent, modelled-other) update: 8-byte record read + written (uint8-hundredths layout, lossless; the "
-                                "reference layout would be 88 B); ncu dram traffic = the algorithmic 16 B/record (profiles/); timed as "
-                                "standalone launches on the trainer's own records at the same shape"}}
+           "l2": "L2 flushed between steps" if small else "back to back: the belief records (4.3 GB at 8192 x 256) outlive no episode in L2",
+           "roofline": roof}
     if cpu_ref_value:
         out["cpu_baseline"] = {"value": cpu_ref_value, "unit": UNIT, "kind": "reference",
                                "sample": "agent-step-equivalent: the reference supports 2 agents only, its 2-agent ia2c.py rate per agent-step "

@@ -23,7 +23,8 @@ def main():
     ok = True
     from ia2c_b200._lib import IA2CError
     for N, E_total, fused, comm in ((2, 64 * world, True, "p2p"), (3, 16 * world, False, "p2p"), (2, 64 * world, True, "nccl"),
-                                    (5, 8 * world, True, "p2p"), (2, 64 * world, True, "p2p-multicast"), (66, 2 * world, False, "p2p")):
+                                    (5, 8 * world, True, "p2p"), (2, 64 * world, True, "p2p-multicast"), (66, 2 * world, False, "p2p"),
+                                    (68, 2 * world, False, "p2p")):   # 66: per-step belief kernel, 68: whole-episode belief kernel
         init = reference_init(N, 5, seed=3)
         try:
             sharded = IA2CTrainer(E_total, n_agents=N, init=init, seed=11, rank=rank, world_size=world, fused_rollout=fused, dumps=True,
