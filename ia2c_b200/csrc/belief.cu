@@ -718,7 +718,7 @@ __global__ void __launch_bounds__(kThreads, 2) belief_pairs_episode_kernel(const
     uint8_t* const belief_dump = FAST ? nullptr : P.belief_dump;
     uint8_t* const pred_dump = FAST ? nullptr : P.pred_dump;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ int queue_n;
+    __shared__ int queue_n2[2];   // flagged records of step t: slot t & 1 (double-buffered like the counts: two barriers per step, not three)
     const int N = P.N, K = P.K, i = blockIdx.y;
     const int KQ = (K + 3) >> 2;
     const int EC = P.envs_per_block;
@@ -730,14 +730,15 @@ __global__ void __launch_bounds__(kThreads, 2) belief_pairs_episode_kernel(const
     double* fa = bpt + A * M * 101;                                  // [M][A]
     float* bpt32 = reinterpret_cast<float*>(fa + M * A);             // [A][M][101]
     float* fcum = bpt32 + ((A * M * 101 + 3) & ~3);                  // [2][M]: F[m][0], F[m][0]+F[m][1]
-    uint32_t* counts = reinterpret_cast<uint32_t*>(fcum + ((2 * M + 3) & ~3));   // [EC] packed 3 x 10 bits
-    uint2* st_mem = reinterpret_cast<uint2*>(counts + ((EC + 3) & ~3));          // [4 * kEpQuads][kThreads] the records of the block
+    uint32_t* counts2 = reinterpret_cast<uint32_t*>(fcum + ((2 * M + 3) & ~3));  // [2][ECp] packed 3 x 10 bits, slot t & 1
+    const int ECp = (EC + 3) & ~3;
+    uint2* st_mem = reinterpret_cast<uint2*>(counts2 + 2 * ECp);                  // [4 * kEpQuads][kThreads] the records of the block
     uint16_t* queue = reinterpret_cast<uint16_t*>(st_mem + 4 * kEpQuads * kThreads);   // [4 * kEpQuads * kThreads] flagged records (cannot overflow)
     uint32_t* seen4 = reinterpret_cast<uint32_t*>(queue + 4 * kEpQuads * kThreads);     // [2][EC][KQ] the others' actions, double-buffered
     pdl_release();
     for (int k = threadIdx.x; k <= 100; k += blockDim.x) tab[k] = __ddiv_rn((double)k, 100.0);
     for (int k = threadIdx.x; k < M * A; k += blockDim.x) fa[k] = P.filter_action[(int64_t)i * M * A + k];
-    if (threadIdx.x == 0) queue_n = 0;
+    if (threadIdx.x < 2) queue_n2[threadIdx.x] = 0;
     __syncthreads();
     for (int x = threadIdx.x; x < A * M * 101; x += blockDim.x) {
         const int seen = x / (M * 101), m = (x / 101) % M, k = x % 101;
@@ -873,11 +874,13 @@ __global__ void __launch_bounds__(kThreads, 2) belief_pairs_episode_kernel(const
     };
     stage_load(0);
     stage_store(0);
-    for (int k = threadIdx.x; k < n_envs; k += blockDim.x) counts[k] = 0u;
+    for (int k = threadIdx.x; k < 2 * ECp; k += blockDim.x) counts2[k] = 0u;
     __syncthreads();
 
     for (int t = 0; t < P.T1; ++t) {
         const int buf = t & 1;
+        uint32_t* counts = counts2 + buf * ECp;
+        int& queue_n = queue_n2[buf];
         if (t + 1 < P.T1) stage_load(t + 1);                       // next step's actions: in flight during this step's arithmetic
         const uint32_t c2 = ((uint32_t)t & 0xFFFFu) | (kStreamBelief << 16);
         const int64_t tbase = (int64_t)t * P.E * N * K;            // index of step t in the per-step tapes / dumps
@@ -963,7 +966,7 @@ __global__ void __launch_bounds__(kThreads, 2) belief_pairs_episode_kernel(const
         }
         if (t + 1 < P.T1) stage_store(buf ^ 1);                    // nobody reads that buffer during this step
         __syncthreads();
-        // ---- partner mode of step t, reset for the next step
+        // ---- partner mode of step t; this slot of the counters is used again at step t + 2 (two barriers from now)
         for (int x = threadIdx.x; x < n_envs; x += blockDim.x) {
             const uint32_t c = counts[x];
             const int n0 = c & 1023, n1 = (c >> 10) & 1023, n2 = c >> 20;
@@ -973,8 +976,7 @@ __global__ void __launch_bounds__(kThreads, 2) belief_pairs_episode_kernel(const
             P.partner_pred[((int64_t)t * P.E + e0 + x) * N + i] = (uint8_t)best;
             counts[x] = 0u;
         }
-        if (threadIdx.x == 0) queue_n = 0;
-        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) queue_n = 0;              // every thread read it before the barrier above
     }
     // ---- the final records
     {
@@ -999,7 +1001,7 @@ int launch_pairs_episode(EpisodePairsArgs& P, cudaStream_t stream) {
     P.envs_per_block = std::max(1, (kEpQuads * kThreads) / KQ);   // <= kEpQuads quads per thread
     const int64_t env_blocks = (P.E + P.envs_per_block - 1) / P.envs_per_block;
     size_t smem = (104 + 3 * M * 101 + M * 3) * sizeof(double) + (((3 * M * 101 + 3) & ~3) + ((2 * M + 3) & ~3)) * sizeof(float) +
-                  (size_t)((P.envs_per_block + 3) & ~3) * sizeof(uint32_t) + (size_t)4 * kEpQuads * kThreads * (sizeof(uint2) + sizeof(uint16_t)) +
+                  (size_t)2 * ((P.envs_per_block + 3) & ~3) * sizeof(uint32_t) + (size_t)4 * kEpQuads * kThreads * (sizeof(uint2) + sizeof(uint16_t)) +
                   (size_t)2 * P.envs_per_block * KQ * sizeof(uint32_t);
     smem = (smem + 15) & ~size_t(15);
     dim3 grid((unsigned)env_blocks, P.N);
