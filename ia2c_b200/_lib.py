@@ -101,6 +101,8 @@ SIGNATURES = {
     "ia2c_host_result_bytes": (C.c_size_t, [_DP]),
     "ia2c_host_pipe_create": (C.c_int, [C.POINTER(vp)]),
     "ia2c_host_pipe_destroy": (C.c_int, [vp]),
+    "ia2c_host_pipe_set_stages": (C.c_int, [vp, i32]),
+    "ia2c_host_stage_stride": (C.c_size_t, [_DP]),
     "ia2c_train_episodes_host": (C.c_int, [_DP, vp, vp, vp, i32, C.POINTER(vp), vp, vp]),
     "ia2c_train_episodes_host_p2p": (C.c_int, [_DP, vp, C.POINTER(PeerDesc), u32, vp, vp, i32, C.POINTER(vp), vp, vp]),
 }

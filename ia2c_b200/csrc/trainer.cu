@@ -739,19 +739,24 @@ extern "C" int ia2c_train_episode_host(const ia2c_episode_desc* d, const float* 
 // episode's losses and returns are read back to its own host slot on the pipe's download stream; one host sync
 // at the end.  The streams and events are owned by a caller-held handle (ia2c_host_pipe_create / _destroy): the
 // library keeps no hidden per-thread state.
+constexpr int kMaxStages = 8;
 struct ia2c_host_pipe {
     cudaStream_t copy = nullptr, down = nullptr;
-    cudaEvent_t copied[2] = {nullptr, nullptr}, consumed[2] = {nullptr, nullptr};
+    cudaEvent_t copied[kMaxStages] = {}, consumed[kMaxStages] = {};          // one pair per staging region
     cudaEvent_t done[2] = {nullptr, nullptr}, downloaded[2] = {nullptr, nullptr};
     int device = -1;
+    int stages = 2;   // staging regions in use: desc.inj_u_action + (stages - 1) consecutive regions at stage_b
 };
 
 extern "C" int ia2c_host_pipe_destroy(ia2c_host_pipe* p) {
     if (!p) return 0;
     if (p->copy) { cudaStreamSynchronize(p->copy); cudaStreamDestroy(p->copy); }
     if (p->down) { cudaStreamSynchronize(p->down); cudaStreamDestroy(p->down); }
+    for (int i = 0; i < kMaxStages; ++i)
+        for (cudaEvent_t ev : {p->copied[i], p->consumed[i]})
+            if (ev) cudaEventDestroy(ev);
     for (int i = 0; i < 2; ++i)
-        for (cudaEvent_t ev : {p->copied[i], p->consumed[i], p->done[i], p->downloaded[i]})
+        for (cudaEvent_t ev : {p->done[i], p->downloaded[i]})
             if (ev) cudaEventDestroy(ev);
     delete p;
     cudaGetLastError();
@@ -765,8 +770,11 @@ extern "C" int ia2c_host_pipe_create(ia2c_host_pipe** out) {
     bool ok = cudaGetDevice(&p->device) == cudaSuccess;
     ok = ok && cudaStreamCreateWithFlags(&p->copy, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaStreamCreateWithFlags(&p->down, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; i < kMaxStages && ok; ++i)
+        for (cudaEvent_t* ev : {&p->copied[i], &p->consumed[i]})
+            ok = ok && cudaEventCreateWithFlags(ev, cudaEventDisableTiming) == cudaSuccess;
     for (int i = 0; i < 2 && ok; ++i)
-        for (cudaEvent_t* ev : {&p->copied[i], &p->consumed[i], &p->done[i], &p->downloaded[i]})
+        for (cudaEvent_t* ev : {&p->done[i], &p->downloaded[i]})
             ok = ok && cudaEventCreateWithFlags(ev, cudaEventDisableTiming) == cudaSuccess;
     if (!ok) {
         const int rc = check_launch("ia2c_host_pipe_create");
@@ -779,11 +787,22 @@ extern "C" int ia2c_host_pipe_create(ia2c_host_pipe** out) {
 
 static inline size_t align8(size_t x) { return (x + 7) & ~size_t(7); }
 
+// Depth of the staging ring: `stages` regions in all (2..8) — desc.inj_u_action plus stages - 1 consecutive regions of
+// ia2c_host_stage_stride(desc) bytes each at stage_b.  More regions let the copy engine run further ahead of the kernels:
+// on a multi-GPU box an episode's kernels wait for the slowest rank in the gradient exchange, and with only two regions
+// every such wait also idles this rank's copy engine.
+extern "C" int ia2c_host_pipe_set_stages(ia2c_host_pipe* p, int32_t stages) {
+    IA2C_REQUIRE(p && stages >= 2 && stages <= kMaxStages, "ia2c_host_pipe_set_stages: stages=%d outside 2..%d", stages, kMaxStages);
+    p->stages = stages;
+    return 0;
+}
+
 extern "C" size_t ia2c_host_tape_bytes(const ia2c_episode_desc* d) {
     if (!d) return 0;
     const size_t n_act = (size_t)(d->T + 1) * d->E * d->N;
     return align8(n_act * sizeof(float)) + n_act * (d->N - 1) * sizeof(double);
 }
+extern "C" size_t ia2c_host_stage_stride(const ia2c_episode_desc* d) { return (ia2c_host_tape_bytes(d) + 255) & ~size_t(255); }
 extern "C" size_t ia2c_host_result_bytes(const ia2c_episode_desc* d) {
     if (!d) return 0;
     return align8(2 * (size_t)d->N * sizeof(float)) + (size_t)d->E * sizeof(double);
@@ -813,7 +832,10 @@ static int episodes_host_impl(const ia2c_episode_desc* d, ia2c_host_pipe* pipe, 
                  "ia2c_train_episodes_host: ep_return must follow loss_out in one result region (ia2c_host_result_bytes)");
     cudaStream_t s = as_stream(stream);
     ia2c_host_pipe& g = *pipe;
-    char* stage[2] = {reinterpret_cast<char*>(const_cast<float*>(d->inj_u_action)), reinterpret_cast<char*>(stage_b)};
+    const int S = g.stages;
+    char* stage[kMaxStages];
+    stage[0] = reinterpret_cast<char*>(const_cast<float*>(d->inj_u_action));
+    for (int b = 1; b < S; ++b) stage[b] = reinterpret_cast<char*>(stage_b) + (size_t)(b - 1) * ia2c_host_stage_stride(d);
     // with a second result region the D2H of episode k runs on its own stream while episode k+1 computes
     char* result[2] = {reinterpret_cast<char*>(d->loss_out), result_b ? reinterpret_cast<char*>(result_b) : reinterpret_cast<char*>(d->loss_out)};
     ia2c_episode_desc e = *d;
@@ -828,21 +850,22 @@ static int episodes_host_impl(const ia2c_episode_desc* d, ia2c_host_pipe* pipe, 
         for (int j = 0; j < 4; ++j) cudaEventCreate(&tr_ev[k][j]);
     auto enqueue = [&]() -> int {
         // the copy stream must not overwrite a staging set that earlier work on `s` may still read
-        if (int rc = cuda_ok(cudaEventRecord(g.consumed[0], s), "cudaEventRecord")) return rc;
-        if (int rc = cuda_ok(cudaEventRecord(g.consumed[1], s), "cudaEventRecord")) return rc;
+        for (int b = 0; b < S; ++b)
+            if (int rc = cuda_ok(cudaEventRecord(g.consumed[b], s), "cudaEventRecord")) return rc;
         for (int k = 0; k < n_episodes; ++k) {
-            const int b = k & 1;
+            const int b = k % S;        // staging region
+            const int rb = k & 1;       // result region
             cudaStreamWaitEvent(g.copy, g.consumed[b], 0);
             if (k < n_traced) cudaEventRecord(tr_ev[k][0], g.copy);
             if (int rc = cuda_ok(cudaMemcpyAsync(stage[b], host_tapes[k], tape_bytes, cudaMemcpyHostToDevice, g.copy), "memcpy H2D uniforms")) return rc;
             if (k < n_traced) cudaEventRecord(tr_ev[k][1], g.copy);
             cudaEventRecord(g.copied[b], g.copy);
             cudaStreamWaitEvent(s, g.copied[b], 0);
-            if (result_b && k >= 2) cudaStreamWaitEvent(s, g.downloaded[b], 0);   // region b was read back before it is rewritten
+            if (result_b && k >= 2) cudaStreamWaitEvent(s, g.downloaded[rb], 0);   // region rb was read back before it is rewritten
             e.inj_u_action = reinterpret_cast<const float*>(stage[b]);
             e.inj_u_belief = reinterpret_cast<const double*>(stage[b] + off_b);
-            e.loss_out = reinterpret_cast<float*>(result[b]);
-            e.ep_return = reinterpret_cast<double*>(result[b] + off_ret);
+            e.loss_out = reinterpret_cast<float*>(result[rb]);
+            e.ep_return = reinterpret_cast<double*>(result[rb] + off_ret);
             e.episode = d->episode + (uint32_t)k;
             if (k < n_traced) cudaEventRecord(tr_ev[k][2], s);
             if (!peers) {
@@ -854,10 +877,10 @@ static int episodes_host_impl(const ia2c_episode_desc* d, ia2c_host_pipe* pipe, 
             cudaEventRecord(g.consumed[b], s);
             char* host_slot = reinterpret_cast<char*>(host_results) + (size_t)k * res_bytes;
             if (result_b) {
-                cudaEventRecord(g.done[b], s);
-                cudaStreamWaitEvent(g.down, g.done[b], 0);
-                if (int rc = cuda_ok(cudaMemcpyAsync(host_slot, result[b], res_bytes, cudaMemcpyDeviceToHost, g.down), "memcpy D2H results")) return rc;
-                cudaEventRecord(g.downloaded[b], g.down);
+                cudaEventRecord(g.done[rb], s);
+                cudaStreamWaitEvent(g.down, g.done[rb], 0);
+                if (int rc = cuda_ok(cudaMemcpyAsync(host_slot, result[rb], res_bytes, cudaMemcpyDeviceToHost, g.down), "memcpy D2H results")) return rc;
+                cudaEventRecord(g.downloaded[rb], g.down);
             } else if (int rc = cuda_ok(cudaMemcpyAsync(host_slot, result[0], res_bytes, cudaMemcpyDeviceToHost, s), "memcpy D2H results")) {
                 return rc;
             }

@@ -311,11 +311,16 @@ class IA2CTrainer:
         tape[off:].view(torch.float64).copy_(torch.as_tensor(np.asarray(u_belief), dtype=torch.float64).reshape(-1))
         return tape
 
+    HOST_STAGES = 4   # depth of the device staging ring of the pipelined host path (ia2c_host_pipe_set_stages)
+
     def _ensure_stage(self):
-        """Two device staging regions for the tapes; the desc's injected-uniform pointers are views of region A."""
+        """Device staging regions for the tapes: region A (the desc's injected-uniform pointers are views of it) and one
+        buffer holding the HOST_STAGES - 1 further regions of the ring (its first region doubles as region B of the NCCL path)."""
         if getattr(self, "_stage", None) is None:
             nbytes = self.host_tape_bytes()
-            self._stage = [torch.empty(nbytes, dtype=torch.uint8, device=self.device) for _ in range(2)]
+            stride = int(self.lib.ia2c_host_stage_stride(C.byref(self.desc)))
+            self._stage_ring = torch.empty(stride * (self.HOST_STAGES - 1), dtype=torch.uint8, device=self.device)
+            self._stage = [torch.empty(nbytes, dtype=torch.uint8, device=self.device), self._stage_ring[:nbytes]]
         self._point_at_stage(0)
 
     def _point_at_stage(self, b):
@@ -346,6 +351,7 @@ class IA2CTrainer:
                 handle = C.c_void_p()
                 with torch.cuda.device(self.device):
                     _lib.check(self.lib.ia2c_host_pipe_create(C.byref(handle)), "ia2c_host_pipe_create")
+                    _lib.check(self.lib.ia2c_host_pipe_set_stages(handle, self.HOST_STAGES), "ia2c_host_pipe_set_stages")
                 self._pipe = handle
             self.desc.episode = self.episode
             with torch.cuda.device(self.device):

@@ -341,6 +341,11 @@ size_t ia2c_host_result_bytes(const ia2c_episode_desc* d);
 typedef struct ia2c_host_pipe ia2c_host_pipe;
 int ia2c_host_pipe_create(ia2c_host_pipe** out);
 int ia2c_host_pipe_destroy(ia2c_host_pipe* pipe);
+/* Depth of the device staging ring (default 2, up to 8): desc.inj_u_action is region 0, stage_b holds `stages - 1` consecutive
+ * regions of ia2c_host_stage_stride(desc) bytes.  A deeper ring lets the H2D copies run further ahead of the kernels (on a
+ * multi-GPU box the kernels wait for the slowest rank twice per episode; with two regions the copy engine waits with them). */
+int ia2c_host_pipe_set_stages(ia2c_host_pipe* pipe, int32_t stages);
+size_t ia2c_host_stage_stride(const ia2c_episode_desc* d);
 /* On any error the call still drains everything it enqueued before returning (no copy is left in flight). */
 int ia2c_train_episodes_host(const ia2c_episode_desc* d, ia2c_host_pipe* pipe, void* stage_b, void* result_b,
                              int32_t n_episodes, const void* const* host_tapes, void* host_results, void* stream);
