@@ -336,6 +336,7 @@ mlp_backward_w1_kernel(const float* __restrict__ x, const float* __restrict__ dz
 // kernels return the dense kernels' bits without the F-wide row: no [rows, F] tensor is ever materialised or read.
 // Only the F-independent tail of the parameters is staged in shared memory; the W1 column is gathered through L1.
 __device__ __forceinline__ void layer1_index(const float* __restrict__ params, const float* ws, int F, int64_t idx, float (&h1)[H]) {
+    idx = idx < 0 ? 0 : (idx >= F ? F - 1 : idx);   // never read outside W1; callers validate the range (Python) or flag it (ia2c_net_update)
 #pragma unroll
     for (int j = 0; j < H; ++j) h1[j] = fmaxf(__fadd_rn(__ldg(params + (int64_t)j * F + idx), ws[j]), 0.f);
 }

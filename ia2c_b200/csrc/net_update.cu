@@ -349,6 +349,16 @@ __global__ void net_update_bump_kernel(int32_t* step_count) {
     if (threadIdx.x == 0 && blockIdx.x == 0) *step_count += 1;
 }
 
+// index inputs: flag class values outside [0, F) (bit 1 of *status) — the gather kernels clamp, so nothing is read out of bounds
+__global__ void index_check_kernel(const int64_t* __restrict__ idx, int64_t rows, int F, int32_t* __restrict__ status) {
+    bool bad = false;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t v = idx[r];
+        bad |= v < 0 || v >= F;
+    }
+    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(status, 2);
+}
+
 size_t dense_smem_bytes(int F, int O) {
     const MlpLayout L(F, O);
     const int n_small = L.P - H * F;
@@ -429,6 +439,10 @@ extern "C" int ia2c_net_update(int32_t kind, float* params, float* grad, float* 
                              A.partials, grid, P, grad, accumulate, A.inv_b, loss_out, params, exp_avg, exp_avg_sq, step_count, lr)))
             return rc;
         return launch_pdl("net_update_bump_kernel", net_update_bump_kernel, dim3(1), dim3(32), 0, s, step_count);
+    }
+    if (idx && status_out) {
+        index_check_kernel<<<(int)std::min<int64_t>(kSMs * 4, (rows + 255) / 256), 256, 0, as_stream(stream)>>>(idx, rows, F, status_out);
+        if ((rc = check_launch("index_check_kernel"))) return rc;
     }
     if (x) rc = ia2c_mlp_forward(params, x, y, h1, rows, F, O, 1, softmax, stream);
     else rc = ia2c_mlp_forward_index(params, idx, y, h1, rows, F, O, softmax, stream);

@@ -301,6 +301,15 @@ def _index_like(act, lead_shape, who):
     return idx
 
 
+def _raise_on_status(status, state_dim):
+    """status word of ia2c_net_update: bit 1 = an index-typed observation outside [0, state_dim) (F.one_hot raises for it too;
+    here the update has already been applied with the offending rows clamped), bit 0 = Categorical's simplex validation."""
+    if status & 2:
+        raise RuntimeError(f"Class values must be in [0, {state_dim}) for an index-typed observation")
+    if status & 1:  # the reference's Categorical validation raises here
+        raise ValueError("Expected parameter probs of distribution Categorical to satisfy the constraint Simplex()")
+
+
 def _no_graph(t):
     return not (isinstance(t, torch.Tensor) and t.requires_grad)
 
@@ -317,8 +326,9 @@ def _fused_update(net, optimizer, kind, obs, act, signal, beta, who):
     p = net.flat
     dev = p.device
     F_, O = net.state_dim, net.action_dim
-    if _is_index_input(obs):
-        idx, flat_idx = _checked_indices(obs, F_, dev)
+    if _is_index_input(obs):   # the range check rides on the update (status bit 1): no extra reduction + host sync here
+        idx = torch.as_tensor(obs).to(dev, torch.int64)
+        flat_idx = idx.reshape(-1).contiguous()
         lead, x2, rows = tuple(idx.shape), None, flat_idx.numel()
     else:
         x = obs if (isinstance(obs, torch.Tensor) and obs.device == dev) else torch.as_tensor(obs).to(dev)
@@ -346,14 +356,14 @@ def _fused_update(net, optimizer, kind, obs, act, signal, beta, who):
         cache[key] = (torch.empty(n, dtype=torch.float32, device=dev), torch.empty((), dtype=torch.float32, device=dev),
                       torch.zeros(1, dtype=torch.int32, device=dev))
     ws, loss, status = cache[key]
-    if kind == 1:
+    if kind == 1 or flat_idx is not None:
         status.zero_()
     with torch.no_grad():
         _lib.check(lib.ia2c_net_update(kind, _lib.ptr(p.data.view(-1)), _lib.ptr(p.grad.view(-1)), _lib.ptr(st["exp_avg"]),
                                        _lib.ptr(st["exp_avg_sq"]), _lib.ptr(st["step"]), _lib.ptr(x2), _lib.ptr(flat_idx), _lib.ptr(a),
                                        _lib.ptr(sig), float(beta), float(group["lr"]), _lib.ptr(loss), _lib.ptr(status), _lib.ptr(ws),
                                        rows, F_, O, _lib.stream_ptr()), "ia2c_net_update")
-    return loss, (status if kind == 1 else None)
+    return loss, (status if (kind == 1 or flat_idx is not None) else None)
 
 
 class CriticNetwork:
@@ -380,7 +390,12 @@ class CriticNetwork:
         if not action_distribution and _no_graph(target) and _no_graph(obs):   # no graph to feed: one fused C call
             fused = _fused_update(self.net, self.optimizer, 0, obs, act, target, 0.0, "CriticNetwork.batch_update")
             if fused is not None:
-                self.losses.append(fused[0].cpu().numpy())
+                if fused[1] is None:
+                    self.losses.append(fused[0].cpu().numpy())
+                else:
+                    vals = torch.stack([fused[0], fused[1][0].to(torch.float32)]).cpu().numpy()   # loss + status: one copy, one sync
+                    _raise_on_status(int(vals[1]), self.net.state_dim)
+                    self.losses.append(vals[0])
                 if len(self.losses) > 20:
                     del self.losses[0]
                 self.critic_loss = np.mean(self.losses)
@@ -502,8 +517,7 @@ class ActorNetwork:
             fused = _fused_update(self.net, self.optimizer, 1, obs, act, adv_f, self.beta, "ActorNetwork.batch_update")
             if fused is not None:
                 vals = torch.stack([fused[0], fused[1][0].to(torch.float32)]).cpu().numpy()   # loss + status: one copy, one sync
-                if int(vals[1]):  # the reference's Categorical validation raises here
-                    raise ValueError("Expected parameter probs of distribution Categorical to satisfy the constraint Simplex()")
+                _raise_on_status(int(vals[1]), self.net.state_dim)
                 self.losses.append(vals[0])
                 if len(self.losses) > 20:
                     del self.losses[0]

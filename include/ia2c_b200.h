@@ -196,7 +196,9 @@ int ia2c_adam_step(float* params, const float* grad, float* grad_accum, float* e
  *                  kind 1 -> grad += gradient, and Adam steps on the running sum (the actor never zeroes it, Q2);
  *   exactly one of x float[rows,F] (dense rows) and idx int64[rows] (class indices standing for one_hot rows);
  *   act int32[rows]; signal float[rows] = target (kind 0) or advantage (kind 1); beta = entropy weight (kind 1);
- *   loss_out float[1] (device); status_out int32[1] (kind 1; set to 1 if a probability row is not a simplex);
+ *   loss_out float[1] (device); status_out int32[1] (zeroed by the caller; required for kind 1, optional for kind 0): bit 0 is set
+ *   if a probability row is not a simplex (kind 1), bit 1 if an idx value lies outside [0, F) (such rows are clamped, never read
+ *   out of bounds — the caller decides what to do with the update);
  *   workspace float[ia2c_net_update_workspace(rows,F,O)].
  * Wide dense inputs (the a2c_test.py shape) take a single-pass kernel that reads x ONCE (bulk async copies into shared
  * memory, both the layer-1 products and the layer-1 weight gradient computed from the staged tile). */

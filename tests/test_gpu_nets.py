@@ -246,6 +246,19 @@ def test_index_input_rejects_out_of_range_classes():
     c = CriticNetwork("c", 500, 6, 1e-3)
     with pytest.raises(RuntimeError, match="Class values"):
         c.run_main(torch.tensor([[3, 500]]))
+    # batch_update validates on the device (no extra reduction + sync): the offending rows are clamped, the call still raises
+    from ia2c_b200.nets import ActorNetwork
+    a = ActorNetwork("a", 500, 6, 1e-3, 0.01)
+    obs = torch.tensor([[3, 499], [0, 7]]).cuda()
+    act, sig = torch.zeros(2, 2, 1), torch.ones(2, 2, 1)
+    c.batch_update(obs, act, sig)
+    a.batch_update(obs, act, sig)
+    bad = obs.clone()
+    bad[1, 1] = 500
+    with pytest.raises(RuntimeError, match="Class values"):
+        c.batch_update(bad, act, sig)
+    with pytest.raises(RuntimeError, match="Class values"):
+        a.batch_update(bad.cpu() - 501, act, sig)
 
 
 @pytest.mark.parametrize("kind,rows,F,O", [(0, 5000, 500, 6), (1, 5000, 500, 6), (0, 1024 + 17, 64, 8), (1, 2048, 128, 3), (1, 4100, 500, 6)])
