@@ -318,7 +318,8 @@ def _fused_update(net, optimizer, kind, obs, act, signal, beta, who):
     """batch_update without a framework graph (target / advantage carries none): ONE C call, ``ia2c_net_update`` —
     forward, loss, backward, Adam — on a cached workspace.  Same arithmetic as the autograd path (the same kernels, or
     for wide dense inputs the single-pass kernel that reads the observations once).  Shares the optimizer's state, so
-    fused and autograd updates can alternate.  -> (loss tensor, status tensor or None), or None if not applicable."""
+    fused and autograd updates can alternate.  -> (loss as numpy float32, status word), read back in one pinned 8-byte copy, or
+    None if not applicable."""
     group = optimizer.param_groups[0]
     if len(optimizer.param_groups) != 1 or tuple(group["betas"]) != (0.9, 0.999) or group["eps"] != 1e-8:
         return None
@@ -353,9 +354,10 @@ def _fused_update(net, optimizer, kind, obs, act, signal, beta, who):
     if key not in cache:
         cache.clear()
         n = int(lib.ia2c_net_update_workspace(rows, F_, O))
-        cache[key] = (torch.empty(n, dtype=torch.float32, device=dev), torch.empty((), dtype=torch.float32, device=dev),
-                      torch.zeros(1, dtype=torch.int32, device=dev))
-    ws, loss, status = cache[key]
+        out = torch.zeros(2, dtype=torch.int32, device=dev)          # [loss (float bits), status]: one 8-byte read-back
+        cache[key] = (torch.empty(n, dtype=torch.float32, device=dev), out[:1].view(torch.float32), out[1:], out,
+                      torch.zeros(2, dtype=torch.int32).pin_memory())
+    ws, loss, status, out, h_out = cache[key]
     if kind == 1 or flat_idx is not None:
         status.zero_()
     with torch.no_grad():
@@ -363,7 +365,10 @@ def _fused_update(net, optimizer, kind, obs, act, signal, beta, who):
                                        _lib.ptr(st["exp_avg_sq"]), _lib.ptr(st["step"]), _lib.ptr(x2), _lib.ptr(flat_idx), _lib.ptr(a),
                                        _lib.ptr(sig), float(beta), float(group["lr"]), _lib.ptr(loss), _lib.ptr(status), _lib.ptr(ws),
                                        rows, F_, O, _lib.stream_ptr()), "ia2c_net_update")
-    return loss, (status if (kind == 1 or flat_idx is not None) else None)
+    h_out.copy_(out, non_blocking=True)
+    torch.cuda.current_stream(dev).synchronize()
+    host = h_out.numpy()
+    return host[:1].view(np.float32)[0].copy(), int(host[1]) if (kind == 1 or flat_idx is not None) else 0
 
 
 class CriticNetwork:
@@ -390,12 +395,8 @@ class CriticNetwork:
         if not action_distribution and _no_graph(target) and _no_graph(obs):   # no graph to feed: one fused C call
             fused = _fused_update(self.net, self.optimizer, 0, obs, act, target, 0.0, "CriticNetwork.batch_update")
             if fused is not None:
-                if fused[1] is None:
-                    self.losses.append(fused[0].cpu().numpy())
-                else:
-                    vals = torch.stack([fused[0], fused[1][0].to(torch.float32)]).cpu().numpy()   # loss + status: one copy, one sync
-                    _raise_on_status(int(vals[1]), self.net.state_dim)
-                    self.losses.append(vals[0])
+                _raise_on_status(fused[1], self.net.state_dim)
+                self.losses.append(fused[0])
                 if len(self.losses) > 20:
                     del self.losses[0]
                 self.critic_loss = np.mean(self.losses)
@@ -516,9 +517,8 @@ class ActorNetwork:
                 adv_f = adv.squeeze(-1)
             fused = _fused_update(self.net, self.optimizer, 1, obs, act, adv_f, self.beta, "ActorNetwork.batch_update")
             if fused is not None:
-                vals = torch.stack([fused[0], fused[1][0].to(torch.float32)]).cpu().numpy()   # loss + status: one copy, one sync
-                _raise_on_status(int(vals[1]), self.net.state_dim)
-                self.losses.append(vals[0])
+                _raise_on_status(fused[1], self.net.state_dim)
+                self.losses.append(fused[0])
                 if len(self.losses) > 20:
                     del self.losses[0]
                 self.actor_loss = np.mean(self.losses)
