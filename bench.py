@@ -706,7 +706,7 @@ def bench_org_n(ctx, args, _lib, name, label, E_total, N, steps, warmup, peak_gb
                                         "frac": 16 * updates / (b_us * 1e-6) / 1e9 / peak_gbs}
         roof["note"] = ("the record stays in registers / shared memory for all T+1 updates of an episode and is written once, so the kernel "
                         "no longer streams: ~1.3 B of unique traffic per update instead of the 16 B (8-byte record read + written) of the per-step "
-                        "kernel — it is bound by instruction issue on the ALU pipe (116 instructions per update, issue slots 61 %: "
+                        "kernel — it is bound by instruction issue on the ALU pipe (108 instructions per update, issue slots 62 %: "
                         "profiles/r02_ncu_summary.md). 'streaming_equivalent' is the HBM rate the per-step kernel (kernels[]: 0.42 of peak standalone) "
                         "would need for the same updates/s")
     else:
