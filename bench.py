@@ -698,7 +698,10 @@ def bench_org_n(ctx, args, _lib, name, label, E_total, N, steps, warmup, peak_gb
     units = E_total * N * T_STEPS
     value = units / (ms * 1e-3)
     roof = {"kernel": ("belief_pairs_episode_kernel<5>" if episode_kernel else ("belief_pairs_table_kernel<5>" if K >= 32 else "belief_pairs_kernel<5>")),
-            "bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs, "traffic": bytes_per_launch,
+            "bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
+            # ncu dram__bytes_read + write of one launch: 498.7 MB per 2.072e9 updates for the episode kernel at 1024 x 256
+            # (profiles/r02_ncu_summary.md 1b), scaled to this shape; = the algorithmic 16 B per update for the per-step kernel
+            "traffic": int(0.2407 * updates) if episode_kernel else bytes_per_launch,
             "bytes_per_launch": bytes_per_launch, "us_per_launch": b_us, "launches_per_episode": launches_per_episode,
             "share_of_step": launches_per_episode * b_us * 1e-3 / ms, "updates_per_s": updates / (b_us * 1e-6)}
     if episode_kernel:
