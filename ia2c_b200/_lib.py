@@ -20,6 +20,7 @@ FLAG_FUSED_CRITIC = 4
 FLAG_GRAD_ONLY = 8
 FLAG_ACTOR_COLUMNS = 16
 FLAG_BELIEF_PER_STEP = 32
+FLAG_ROLLOUT_PER_STEP = 64
 BELIEF_RECORD = 8
 ABI_VERSION = 2
 ACTOR_P = 105

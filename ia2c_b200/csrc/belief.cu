@@ -392,8 +392,8 @@ __global__ void __launch_bounds__(kThreads, 2) belief_pairs_table_kernel(const _
             for (int b = 0; b < kBatch; ++b) {
                 const bool ok = x0 + b * (int)blockDim.x < words;
                 ww[b] = w;
-                lo[b] = ok ? __ldg(src + el * NW + w) : 0u;
-                hi[b] = (ok && w + 1 < NW) ? __ldg(src + el * NW + w + 1) : 0u;
+                lo[b] = ok ? __ldcg(src + el * NW + w) : 0u;
+                hi[b] = (ok && w + 1 < NW) ? __ldcg(src + el * NW + w + 1) : 0u;
                 el += s_el; w += s_w;
                 if (w >= KQ) { w -= KQ; ++el; }
             }
@@ -854,8 +854,8 @@ __global__ void __launch_bounds__(kThreads, 2) belief_pairs_episode_kernel(const
 #pragma unroll
         for (int s_ = 0; s_ < kEpQuads; ++s_) {
             const bool ok = stage_src[s_] != 0xFFFFFFFFu;
-            stage_lo[s_] = ok ? __ldg(src + stage_src[s_]) : 0u;
-            stage_hi[s_] = (ok && !(stage_sel[s_] >> 31)) ? __ldg(src + stage_src[s_] + 1) : 0u;
+            stage_lo[s_] = ok ? __ldcg(src + stage_src[s_]) : 0u;
+            stage_hi[s_] = (ok && !(stage_sel[s_] >> 31)) ? __ldcg(src + stage_src[s_] + 1) : 0u;
         }
     };
     auto stage_store = [&](int buf) {

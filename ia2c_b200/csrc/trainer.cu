@@ -170,6 +170,125 @@ __global__ void __launch_bounds__(kActorThreads) actor_step_kernel(StepArgs S) {
     }
 }
 
+// rollout_many_kernel (9 <= N <= 256): the T+1 env / actor steps of an episode in ONE persistent launch instead of 2(T+1)
+// launches of env_step_kernel / actor_step_kernel — same functions, same order of operations, same Philox counters, so the
+// trajectory bytes are identical.  Envs are independent: a block owns a chunk of envs for the whole episode, thread = agent
+// (its actor in registers, FFMA2), and a step is
+//   (1) every agent samples its action for each env of the chunk; per-warp action counts by ballots;
+//   (2) the chunk's first threads (one per env) total the counts, advance the env (transition, fp64 reward recurrence,
+//       same-step autoreset) and publish the next observation classes;
+//   (3) every agent derives the mode of the OTHERS' actions (partner_true)
+// with two block barriers per step.  The belief update of the whole episode follows as one kernel (belief.cu).
+constexpr int kManyMaxEnvs = 32;     // envs per block
+__global__ void __launch_bounds__(256) rollout_many_kernel(const __grid_constant__ ia2c_episode_desc d, int envs_per_block) {
+    extern __shared__ __align__(16) unsigned char many_smem[];
+    const int N = d.N, T = d.T, i = threadIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    const int64_t E = d.E, e0 = (int64_t)blockIdx.x * envs_per_block;
+    const int EC = (int)min((int64_t)envs_per_block, E - e0);
+    uint32_t* warp_cnt = reinterpret_cast<uint32_t*>(many_smem);                 // [EC][n_warps] packed 3 x 10 bits
+    uint32_t* tot_cnt = warp_cnt + kManyMaxEnvs * 8;                              // [EC]
+    int* cls_s = reinterpret_cast<int*>(tot_cnt + kManyMaxEnvs);                  // [EC] prev | cur << 2
+    uint8_t* act_s = reinterpret_cast<uint8_t*>(cls_s + kManyMaxEnvs);            // [EC][blockDim]
+    pdl_prologue();
+    const bool agent = i < N;
+    RegNet<A> net;
+    if (agent && !d.inj_actions) load_regnet<A>(net, d.actor_params + (int64_t)i * kActorP);
+    // env state of env el lives in the registers of thread el
+    int s = 2, prev_cls = 1, cur_cls = 1, elapsed = 0;
+    double hist = 0.0, ep_ret = 0.0;
+    const bool owner = i < EC;
+    if (owner) {
+        cls_s[i] = 1 | (1 << 2);
+        float* o = d.obs + (e0 + i) * F;
+#pragma unroll
+        for (int k = 0; k < F; ++k) o[k] = (k == 1 || k == 4) ? 1.f : 0.f;        // reset observation [0,1,0,0,1,0] (Org.py:128-148)
+    }
+    __syncthreads();
+    for (int t = 0; t <= T; ++t) {
+        // ---- (1) actions of step t
+        for (int el = 0; el < EC; ++el) {
+            const int64_t e = e0 + el;
+            int a = 3;   // no action (threads beyond N)
+            if (agent) {
+                const int64_t row = ((int64_t)t * E + e) * N + i;
+                if (d.inj_actions) {
+                    a = d.inj_actions[row];
+                } else {
+                    const int packed = cls_s[el];
+                    float x[F], y[A];
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        x[k] = (k == (packed & 3)) ? 1.f : 0.f;
+                        x[3 + k] = (k == (packed >> 2)) ? 1.f : 0.f;
+                    }
+                    forward_regnet<A>(net, x, y);
+                    softmax_inplace<A>(y);
+                    const float u = d.inj_u_action ? d.inj_u_action[row]
+                                                   : philox_uniform_f32(d.seed, kStreamAction, d.episode, (uint32_t)t,
+                                                                        (uint64_t)((d.env_offset + e) * N + i));
+                    a = sample_inverse_cdf<A>(y, u);
+                }
+                d.act[row] = (uint8_t)a;
+            }
+            act_s[el * blockDim.x + i] = (uint8_t)a;
+            const uint32_t c0 = __popc(__ballot_sync(0xffffffffu, a == 0)), c1 = __popc(__ballot_sync(0xffffffffu, a == 1)),
+                           c2 = __popc(__ballot_sync(0xffffffffu, a == 2));
+            if (lane == 0) warp_cnt[el * 8 + warp] = c0 | (c1 << 10) | (c2 << 20);
+        }
+        __syncthreads();
+        // ---- (2) totals, env transition (steps 0..T-1 advance the env; after step T only partner_true[T] is due)
+        if (owner) {
+            uint32_t packed = 0u;
+            for (int w = 0; w < n_warps; ++w) packed += warp_cnt[i * 8 + w];
+            tot_cnt[i] = packed;
+            if (t < T) {
+                const int64_t e = e0 + i;
+                const int c0 = packed & 1023, c1 = (packed >> 10) & 1023, c2 = (packed >> 20) & 1023;
+                int s2;
+                double base;
+                org_transition(s, c0, c1, c2, N, s2, base);
+                double r = org_reward(base, hist);
+                prev_cls = cur_cls;
+                cur_cls = org_obs_class(s2);
+                d.reward[(int64_t)t * E + e] = (float)r;          // float32(r) as stored by ia2c.py:99
+                ep_ret += r;                                     // fp64, in step order (ia2c.py:102)
+                if (d.state_trace) d.state_trace[(int64_t)t * E + e] = s2;
+                if (d.reward_f64) d.reward_f64[(int64_t)t * E + e] = r;
+                ++elapsed;
+                if (d.max_episode_steps > 0 && elapsed >= d.max_episode_steps) {   // same-step autoreset (Q14)
+                    s2 = 2; r = 0.0; prev_cls = 1; cur_cls = 1; elapsed = 0;
+                }
+                s = s2;
+                hist = r;
+                cls_s[i] = prev_cls | (cur_cls << 2);
+                float* o = d.obs + ((int64_t)(t + 1) * E + e) * F;
+#pragma unroll
+                for (int k = 0; k < F; ++k) o[k] = (k < 3 ? k == prev_cls : k - 3 == cur_cls) ? 1.f : 0.f;
+            }
+        }
+        __syncthreads();
+        // ---- (3) mode of the others' actions at step t
+        if (agent) {
+            for (int el = 0; el < EC; ++el) {
+                const uint32_t packed = tot_cnt[el];
+                const int a = act_s[el * blockDim.x + i];
+                const int c0 = packed & 1023, c1 = (packed >> 10) & 1023, c2 = (packed >> 20) & 1023;
+                d.partner_true[((int64_t)t * E + e0 + el) * N + i] = (uint8_t)mode3(c0 - (a == 0), c1 - (a == 1), c2 - (a == 2));
+            }
+        }
+        // (the next step's writes to warp_cnt / act_s come after these reads only per thread for act_s — own entries — and after
+        //  the next barrier for tot_cnt; warp_cnt is rewritten before that barrier but was last read before this step's second one)
+    }
+    if (owner) {   // persist the final env state exactly as the per-step path leaves it
+        const int64_t e = e0 + i;
+        d.env_state[e] = s;
+        d.env_hist[e] = hist;
+        d.env_elapsed[e] = elapsed;
+        d.ep_return[e] = ep_ret;
+        *reinterpret_cast<uchar2*>(d.env_cls + 2 * e) = make_uchar2((unsigned char)prev_cls, (unsigned char)cur_cls);
+    }
+}
+
 // ---- gradient kernels: one thread per (agent, env, time chunk), packed fp32 math (mlp_f2.cuh) ----------
 // next_obs[t] IS obs[t+1] (trajectory layout), so a thread that walks a chunk [t0,t1) of one env's
 // time axis evaluates the critic ONCE per observation (L+1 forwards for L rows instead of 2L) and, in the
@@ -468,6 +587,18 @@ extern "C" int ia2c_rollout(const ia2c_episode_desc* d, void* stream) {
         }
         return rollout_fused_launch(d, s);
     }
+    const bool episode_beliefs = !(d->flags & IA2C_FLAG_BELIEF_PER_STEP) && ia2c_belief_supports_episode(d->N, d->M);
+    if (episode_beliefs && !(d->flags & IA2C_FLAG_ROLLOUT_PER_STEP) && d->N <= 256) {
+        // ONE persistent kernel for the T+1 env / actor steps, then ONE kernel for the episode's belief updates
+        const int threads = ((d->N + 31) / 32) * 32;
+        int epb = (int)std::min<int64_t>(kManyMaxEnvs, std::max<int64_t>(1, (d->E + 2 * kSMs - 1) / (2 * kSMs)));
+        epb = std::min(epb, threads);            // one owner thread per env of the chunk
+        const int64_t grid = (d->E + epb - 1) / epb;
+        const size_t smem = (size_t)kManyMaxEnvs * (8 + 1 + 1) * 4 + (size_t)kManyMaxEnvs * threads;
+        if (int rc = launch_pdl("rollout_many_kernel", rollout_many_kernel, dim3((unsigned)grid), dim3(threads), smem, s, *d, epb)) return rc;
+        return ia2c_belief_update_pairs_episode(d->belief_records, d->filter_action, d->act, d->inj_u_belief, d->pred_dump, d->belief_dump,
+                                                d->partner_pred, d->E, d->N, d->M, d->T + 1, d->seed, d->episode, d->env_offset, stream);
+    }
     StepArgs S;
     S.d = *d;
     int G = 1;
@@ -483,7 +614,6 @@ extern "C" int ia2c_rollout(const ia2c_episode_desc* d, void* stream) {
     // Nothing reads a belief before the update phase (ia2c.py:72-102 vs :104-121), so with many modelled others the T+1 env /
     // actor steps run first and ONE kernel then carries every belief record through the whole episode in registers
     // (belief.cu: belief_pairs_episode_kernel) instead of streaming the records once per step.
-    const bool episode_beliefs = !(d->flags & IA2C_FLAG_BELIEF_PER_STEP) && ia2c_belief_supports_episode(d->N, d->M);
     for (int t = 0; t <= d->T + 1; ++t) {
         S.t = t;
         if (int rc = launch_pdl("env_step_kernel", env_step_kernel, dim3(blocks), dim3(kRolloutThreads), 0, s, S)) return rc;

@@ -50,7 +50,7 @@ class IA2CTrainer:
     def __init__(self, num_envs, n_agents=2, n_models=5, steps_per_episode=30, max_episode_steps=30,
                  lr_critic=0.0002, lr_actor=0.0001, beta=0.001, gamma=0.9, seed=0, device=None,
                  rank=0, world_size=1, process_group=None, dumps=False, fused_rollout=None, fused_critic=None,
-                 init=None, comm="auto", actor_kernel="auto", belief_kernel="auto"):
+                 init=None, comm="auto", actor_kernel="auto", belief_kernel="auto", rollout_kernel="auto"):
         _lib.require_cuda()
         if actor_kernel not in ("auto", "pipe", "columns"):
             raise ValueError("actor_kernel must be 'auto', 'pipe' or 'columns'")
@@ -111,6 +111,7 @@ class IA2CTrainer:
         # kernel where the library supports it (N >= 33, N % 4 == 0), "step" streams the records once per step (A/B, parity)
         d.flags = ((_lib.FLAG_FUSED_ROLLOUT if fused_rollout else 0) | (_lib.FLAG_SKIP_ADAM if self.world > 1 else 0) |
                    (_lib.FLAG_BELIEF_PER_STEP if belief_kernel == "step" else 0) |
+                   (_lib.FLAG_ROLLOUT_PER_STEP if rollout_kernel == "step" else 0) |   # N > 8: per-step env / actor kernels (A/B, parity)
                    (_lib.FLAG_FUSED_CRITIC if (fused_rollout and fused_critic) else 0) |
                    (_lib.FLAG_ACTOR_COLUMNS if actor_kernel == "columns" else 0))
         for name in ("actor_params", "actor_grad", "actor_grad_accum", "actor_m", "actor_v", "critic_params",

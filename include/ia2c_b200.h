@@ -263,6 +263,8 @@ typedef struct ia2c_episode_desc {
                                        ia2c_allreduce_adam then reduces, exchanges and steps */
 #define IA2C_FLAG_ACTOR_COLUMNS 16  /* actor phase: use the time-chunk column kernel instead of the pipelined one (A/B, parity tests) */
 #define IA2C_FLAG_SKIP_ADAM     2   /* stop after writing gradients (multi-GPU: all-reduce, then ia2c_adam_step) */
+#define IA2C_FLAG_ROLLOUT_PER_STEP 64 /* rollout (N > 8): one env_step + one actor_step kernel per step instead of the persistent
+                                      * rollout_many_kernel (9 <= N <= 256 with the whole-episode belief kernel) — A/B and parity tests */
 #define IA2C_FLAG_BELIEF_PER_STEP 32 /* rollout (N > 8): one belief kernel per step (ia2c_belief_update_pairs) instead of the
                                       * whole-episode kernel (ia2c_belief_update_pairs_episode) — A/B and parity tests */
 

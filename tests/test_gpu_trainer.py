@@ -297,19 +297,21 @@ def test_full_size_properties(E, N):
     assert a["env_state"].min() >= 0 and a["env_state"].max() <= 4
 
 
-@pytest.mark.parametrize("E,N,T", [(6, 64, 7), (3, 132, 4)])
+@pytest.mark.parametrize("E,N,T", [(6, 64, 7), (3, 132, 4), (700, 36, 6), (41, 256, 3)])
 def test_whole_episode_belief_kernel_equals_the_per_step_rollout(E, N, T):
     """N > 8 rollout: env / actor steps first and ONE belief kernel for the whole episode (default where the library supports it)
     against one belief kernel per step (belief_kernel="step"): every rollout output byte and every update output bit."""
     M = 5
     init = _random_init(N, M, seed=N)
-    a = make_trainer(E, N, M, init, seed=8, steps_per_episode=T, max_episode_steps=T, belief_kernel="step")
-    b = make_trainer(E, N, M, init, seed=8, steps_per_episode=T, max_episode_steps=T)
-    assert (a.desc.flags & 32) and not (b.desc.flags & 32)
+    a = make_trainer(E, N, M, init, seed=8, steps_per_episode=T, max_episode_steps=min(T, 5), belief_kernel="step")   # 3 kernels per step
+    b = make_trainer(E, N, M, init, seed=8, steps_per_episode=T, max_episode_steps=min(T, 5))   # rollout_many_kernel + episode belief kernel
+    c = make_trainer(E, N, M, init, seed=8, steps_per_episode=T, max_episode_steps=min(T, 5), rollout_kernel="step")  # per-step env/actor + episode beliefs
+    assert (a.desc.flags & 32) and not (b.desc.flags & (32 | 64)) and (c.desc.flags & 64)
     for ep in range(2):
-        la, lb = a.train_episode(sync_stats=True), b.train_episode(sync_stats=True)
-        for name in ROLLOUT_OUTPUTS + ("belief_records",):
-            assert np.array_equal(host(getattr(a, name)), host(getattr(b, name))), (name, ep)
-        for name in UPDATE_OUTPUTS:
-            assert np.array_equal(host(getattr(a, name)), host(getattr(b, name))), (name, ep)
-        assert np.array_equal(la["ep_return"], lb["ep_return"])
+        la, lb, lc = a.train_episode(sync_stats=True), b.train_episode(sync_stats=True), c.train_episode(sync_stats=True)
+        for other in (b, c):
+            for name in ROLLOUT_OUTPUTS + ("belief_records",):
+                assert np.array_equal(host(getattr(a, name)), host(getattr(other, name))), (name, ep)
+            for name in UPDATE_OUTPUTS:
+                assert np.array_equal(host(getattr(a, name)), host(getattr(other, name))), (name, ep)
+        assert np.array_equal(la["ep_return"], lb["ep_return"]) and np.array_equal(la["ep_return"], lc["ep_return"])
