@@ -486,23 +486,20 @@ def bench_headline(ctx, args, _lib, peak_gbs, peak_src, sampler):
     # ---- region A: R blocks of K steps, L2 flushed between steps (outside the per-step events)
     def adv():
         tr.episode += 1
-    blocks, roll_ms, step_ms_own = [], 0.0, 0.0
+    blocks = []
     launches0 = _lib.launch_count()
-    if ctx.world == 1:
-        fns = [tr.rollout, tr.update]
-    else:   # one C call per episode per rank (the two gradient exchanges are kernels in the same stream)
-        fns = [tr.train_episode]
-    for r in range(R):
-        if ctx.world == 1:
-            total, segs = time_steps_flushed(ctx, fns + [adv], K)
-            roll_ms += segs[0]
-        else:
-            total, segs = time_steps_flushed(ctx, fns, K)
-        step_ms_own += total
+    for r in range(R):   # one C call per episode per rank (world > 1: the two gradient exchanges are kernels in the same stream)
+        total, _ = time_steps_flushed(ctx, [tr.train_episode], K)
         blocks.append(ctx.max_over_ranks(total))
     launches = (_lib.launch_count() - launches0) // R
     tr.check_comm()
     total_ms = statistics.median(blocks)
+    # the rollout kernel on its own (single rank): the same steps as three calls with an event between the phases -- the
+    # records cost the programmatic-launch overlap between the kernels (~2 us each), so this pass feeds `roofline` only
+    roll_ms = seg_ms = 0.0
+    if ctx.world == 1:
+        seg_ms, segs = time_steps_flushed(ctx, [tr.rollout, tr.update, adv], K)
+        roll_ms = segs[0]
     # ---- region B: the same K steps back to back, one event pair (no flush)
     b2b = [ctx.max_over_ranks(time_block(ctx, tr.train_episode, K)) for _ in range(R)]
     tr.check_comm()
@@ -624,8 +621,8 @@ def bench_headline(ctx, args, _lib, peak_gbs, peak_src, sampler):
     if fused:   # + the critic-gradient partials the fused critic stage writes (one 148-float row per block and agent)
         traj_bytes += (E_gpu * (2 if N <= 2 else 4 if N <= 4 else 8) // 32) * N * 148 * 4
     if ctx.world == 1:
-        rollout_us = roll_ms / (K * R) * 1e3
-        share = roll_ms / step_ms_own
+        rollout_us = roll_ms / K * 1e3
+        share = roll_ms / seg_ms
     else:
         rollout_us, share = None, None
     if rollout_us:
@@ -699,9 +696,9 @@ def bench_org_n(ctx, args, _lib, name, label, E_total, N, steps, warmup, peak_gb
     value = units / (ms * 1e-3)
     roof = {"kernel": ("belief_pairs_episode_kernel<5>" if episode_kernel else ("belief_pairs_table_kernel<5>" if K >= 32 else "belief_pairs_kernel<5>")),
             "bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
-            # ncu dram__bytes_read + write of one launch: 498.7 MB per 2.072e9 updates for the episode kernel at 1024 x 256
+            # ncu dram__bytes_read + write of one launch: 500.1 MB per 2.072e9 updates for the episode kernel at 1024 x 256
             # (profiles/r02_ncu_summary.md 1b), scaled to this shape; = the algorithmic 16 B per update for the per-step kernel
-            "traffic": int(0.2407 * updates) if episode_kernel else bytes_per_launch,
+            "traffic": int(0.2416 * updates) if episode_kernel else bytes_per_launch,
             "bytes_per_launch": bytes_per_launch, "us_per_launch": b_us, "launches_per_episode": launches_per_episode,
             "share_of_step": launches_per_episode * b_us * 1e-3 / ms, "updates_per_s": updates / (b_us * 1e-6)}
     if episode_kernel:
@@ -709,7 +706,7 @@ def bench_org_n(ctx, args, _lib, name, label, E_total, N, steps, warmup, peak_gb
                                         "frac": 16 * updates / (b_us * 1e-6) / 1e9 / peak_gbs}
         roof["note"] = ("the record stays in registers / shared memory for all T+1 updates of an episode and is written once, so the kernel "
                         "no longer streams: ~1.3 B of unique traffic per update instead of the 16 B (8-byte record read + written) of the per-step "
-                        "kernel — it is bound by instruction issue on the ALU pipe (108 instructions per update, issue slots 62 %: "
+                        "kernel — it is bound by instruction issue on the ALU pipe (116 instructions per update, issue slots 71 %: "
                         "profiles/r02_ncu_summary.md). 'streaming_equivalent' is the HBM rate the per-step kernel (kernels[]: 0.42 of peak standalone) "
                         "would need for the same updates/s")
     else:

@@ -249,10 +249,10 @@ __global__ void debug_divide_kernel(const double* __restrict__ a, const double* 
 //  (2) the stored posterior is rint(100 * bp[m]/S) and the predicted action is a comparison of u with the cumulative
 //      mixture — both are DECISIONS, so they are first taken in fp32 (table lookups, one MUFU.RCP, FFMA) together with
 //      a rigorous distance-to-the-boundary test: the fp32 quotient 100*bp/S is within 6e-5 of the fp64 value
-//      (9 roundings of 2^-24 relative on a value <= 100), so a rounding is accepted only when it is more than 2.5e-4
+//      (9 roundings of 2^-24 relative on a value <= 100), so a rounding is accepted only when it is more than 1e-4
 //      away from a half-integer; the inverse-CDF comparison u*S < sum_m bp[m]*Fcum[m][a] is accepted only when the
 //      two sides differ by more than 1e-5*S (their fp32 errors are below 1e-6*S each);
-//  (3) a record that fails either test (~0.3 % of them) is recomputed with the exact fp64 sequence of belief_core on
+//  (3) a record that fails either test (~0.1 % of them) is recomputed with the exact fp64 sequence of belief_core on
 //      the fp64 table (same operands, same order, IEEE division) — bit-identical to belief_pairs_kernel and to the
 //      oracle by construction, and checked against both by tests/test_gpu_belief.py.
 // Thread = the FOUR modelled-other slots 4s..4s+3 of one (env, agent): they share one Philox block (common.cuh:
@@ -262,7 +262,9 @@ __global__ void debug_divide_kernel(const double* __restrict__ a, const double* 
 // FAST = the steady-state call of the rollout (device Philox, no dumps, priors from the records): the optional
 // pointers are compiled out instead of costing a predicated-off instruction each per record.
 constexpr float kRoundMagic = 12582912.f;       // 1.5 * 2^23: x + magic has rint(x) in its low mantissa bits
-constexpr float kHalfWindow = 0.5f - 2.5e-4f;    // |100*b - rint(100*b)| above this -> exact path
+// Rounding screen: x32 = bp32 * (rcp.approx(S32) * 100) differs from the real 100*bp/S by at most 9 * 2^-24 relative (table entry
+// 1, four fp32 adds + their inputs 5, rcp.approx 2, the *100 1 — units of 2^-24), i.e. 5.4e-5 at x = 100; the window is 1.9 x that.
+constexpr float kHalfWindow = 0.5f - 1.0e-4f;    // |100*b - rint(100*b)| above this -> exact path
 constexpr float kCdfWindow = 1e-5f;              // |u*S - cumulative| below this * S -> exact path
 
 template <int M>
@@ -313,6 +315,35 @@ __device__ __forceinline__ float lds_f32(uint32_t addr) {
     float v;
     asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
     return v;
+}
+
+// Second-level rounding screen of ONE record, run by the rare lanes whose first-level test (constant window kHalfWindow)
+// fired: the same fp32 quantities, but every value is tested against its OWN error bound — x32 is within 9 * 2^-24 * x of the
+// real quotient, so a rounding is safe when |x32 - rint(x32)| < 0.5 - 1e-6 * (rint(x32) + 1) (1.9 x the bound).  Cuts the
+// records that reach the fp64 sequence by ~5x.  -> true when the record still needs the exact path.
+template <int M>
+__device__ __noinline__ bool belief_refine_rounding(uint32_t row_s, uint2 raw) {
+    float bp[M];
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+        const uint32_t k = ((m < 4 ? raw.x : raw.y) >> (8 * (m & 3))) & 0xFFu;
+        bp[m] = lds_f32(row_s + 4u * k + (uint32_t)(m * 101 * 4));
+    }
+    float S = bp[0];
+#pragma unroll
+    for (int m = 1; m < M; ++m) S = __fadd_rn(S, bp[m]);
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(S));
+    const float r100 = __fmul_rn(r, 100.f);
+    bool exact = false;
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+        const float kf = __fmaf_rn(bp[m], r100, kRoundMagic);
+        const float nk = __fsub_rn(kRoundMagic, kf);                  // -rint(x32)
+        const float d = __fmaf_rn(bp[m], r100, nk);
+        exact |= fabsf(d) > __fmaf_rn(nk, 1e-6f, 0.5f - 1e-6f);      // 0.5 - 1e-6 * (rint + 1)
+    }
+    return exact;
 }
 
 // Philox4x32-10 with precomputed round keys (identical to philox4x32_10: key_r = key_0 + r * W)
@@ -693,9 +724,13 @@ int launch_pairs_table(PairsArgs& P, cudaStream_t stream) {
 // the cp.async ring and the table build are paid once per record-episode instead of once per update.  Same screen, same
 // exact sequence, same Philox counters as the per-step kernel: bit-identical records, predictions and partner modes
 // (tests/test_gpu_belief.py compares the two kernels and the oracle).
-// Block = (agent, chunk of envs) with <= 4 quads (16 records) per thread; per step: stage the others' actions (double
-// buffered), screen, defer the ~0.3 % flagged records to a dense exact pass that PATCHES the owners' registers before the
-// next step, reduce the predicted-action counts per env, write partner_pred[t].
+// Block = (agent, chunk of envs); every WARP owns whole envs (<= 4 quads = 16 records per lane) and runs the episode on its
+// own: no block barrier inside the step loop.  Per step a warp stages the others' actions of the next step (registers ->
+// its own shared-memory slots), screens its records, recomputes the flagged ones (~0.1 %) with the exact fp64 sequence —
+// its own lanes, one record each, fixed in place before the next step reads them — reduces the predicted-action counts of
+// its envs and writes partner_pred[t].  While one warp sits in an exact evaluation (a ~3000-cycle fp64 chain) the SM's
+// other 15 warps keep screening: with the block-wide exact pass this kernel had first, 1.1 of every 5 cycles per issued
+// instruction were barrier stalls (profiles/r02_ncu_summary.md §1b).
 struct EpisodePairsArgs {
     uint8_t* records;              // [E,N,K,8] out: the posteriors after step T (+ predicted action of step T in byte 6)
     const double* filter_action;   // [N,M,3]
@@ -705,11 +740,13 @@ struct EpisodePairsArgs {
     uint8_t* belief_dump;          // [T1,E,N,K,M] or null
     uint8_t* partner_pred;         // [T1,E,N]
     int64_t E, env_offset;
-    int N, K, T1, envs_per_block;
+    int N, K, T1, envs_per_warp;
     uint32_t episode;
     uint32_t rk[20];
 };
-constexpr int kEpQuads = 4;        // quads per thread
+constexpr int kEpQuads = 4;                    // quads per lane
+constexpr int kEpWarps = kThreads / 32;
+constexpr int kEpWarpQuads = 32 * kEpQuads;    // quad slots of a warp: an env's KQ quads must fit (N <= 512)
 
 template <int M, bool FAST>
 __global__ void __launch_bounds__(kThreads, 2) belief_pairs_episode_kernel(const __grid_constant__ EpisodePairsArgs P) {
@@ -718,27 +755,27 @@ __global__ void __launch_bounds__(kThreads, 2) belief_pairs_episode_kernel(const
     uint8_t* const belief_dump = FAST ? nullptr : P.belief_dump;
     uint8_t* const pred_dump = FAST ? nullptr : P.pred_dump;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ int queue_n2[2];   // flagged records of step t: slot t & 1 (double-buffered like the counts: two barriers per step, not three)
+    __shared__ int queue_n_w[kEpWarps];   // flagged records of the warp's current step
     const int N = P.N, K = P.K, i = blockIdx.y;
     const int KQ = (K + 3) >> 2;
-    const int EC = P.envs_per_block;
-    const int64_t e0 = (int64_t)blockIdx.x * EC;
-    const int n_envs = (int)min((int64_t)EC, P.E - e0);
-    const int lane = threadIdx.x & 31;
+    const int EW = P.envs_per_warp, EWp = (EW + 3) & ~3;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t e0 = ((int64_t)blockIdx.x * kEpWarps + warp) * EW;                 // the warp's first env
+    const int n_envs = (int)max((int64_t)0, min((int64_t)EW, P.E - e0));
     double* tab = reinterpret_cast<double*>(smem_raw);               // [104]   k/100
     double* bpt = tab + 104;                                         // [A][M][101]
     double* fa = bpt + A * M * 101;                                  // [M][A]
     float* bpt32 = reinterpret_cast<float*>(fa + M * A);             // [A][M][101]
     float* fcum = bpt32 + ((A * M * 101 + 3) & ~3);                  // [2][M]: F[m][0], F[m][0]+F[m][1]
-    uint32_t* counts2 = reinterpret_cast<uint32_t*>(fcum + ((2 * M + 3) & ~3));  // [2][ECp] packed 3 x 10 bits, slot t & 1
-    const int ECp = (EC + 3) & ~3;
-    uint2* st_mem = reinterpret_cast<uint2*>(counts2 + 2 * ECp);                  // [4 * kEpQuads][kThreads] the records of the block
-    uint16_t* queue = reinterpret_cast<uint16_t*>(st_mem + 4 * kEpQuads * kThreads);   // [4 * kEpQuads * kThreads] flagged records (cannot overflow)
-    uint32_t* seen4 = reinterpret_cast<uint32_t*>(queue + 4 * kEpQuads * kThreads);     // [2][EC][KQ] the others' actions, double-buffered
+    uint32_t* counts = reinterpret_cast<uint32_t*>(fcum + ((2 * M + 3) & ~3)) + warp * EWp;   // [warps][EWp] packed 3 x 10 bits
+    uint2* st_mem = reinterpret_cast<uint2*>(counts - warp * EWp + kEpWarps * EWp);            // [4 * kEpQuads][kThreads] the records
+    uint16_t* queue = reinterpret_cast<uint16_t*>(st_mem + 4 * kEpQuads * kThreads) + warp * (4 * kEpWarpQuads);   // [warps][records of a warp]
+    uint32_t* seen4 = reinterpret_cast<uint32_t*>(queue - warp * (4 * kEpWarpQuads) + 4 * kEpQuads * kThreads);    // [kEpQuads][kThreads] the others' actions
     pdl_release();
     for (int k = threadIdx.x; k <= 100; k += blockDim.x) tab[k] = __ddiv_rn((double)k, 100.0);
     for (int k = threadIdx.x; k < M * A; k += blockDim.x) fa[k] = P.filter_action[(int64_t)i * M * A + k];
-    if (threadIdx.x < 2) queue_n2[threadIdx.x] = 0;
+    if (threadIdx.x < kEpWarps) queue_n_w[threadIdx.x] = 0;
+    for (int k = threadIdx.x; k < kEpWarps * EWp; k += blockDim.x) (counts - warp * EWp)[k] = 0u;
     __syncthreads();
     for (int x = threadIdx.x; x < A * M * 101; x += blockDim.x) {
         const int seen = x / (M * 101), m = (x / 101) % M, k = x % 101;
@@ -754,14 +791,16 @@ __global__ void __launch_bounds__(kThreads, 2) belief_pairs_episode_kernel(const
         fcum[M + threadIdx.x] = (float)__dadd_rn(fa[threadIdx.x * A], fa[threadIdx.x * A + 1]);
     }
     pdl_wait();
-    __syncthreads();
+    __syncthreads();   // the last block-wide barrier: from here on the warps run independently
+    if (n_envs == 0) return;
     float f0[M], f01[M];
 #pragma unroll
     for (int m = 0; m < M; ++m) { f0[m] = fcum[m]; f01[m] = fcum[M + m]; }
     const uint32_t bpt32_s = (uint32_t)__cvta_generic_to_shared(bpt32);
     const float2 magic2 = make_float2(kRoundMagic, kRoundMagic), minus1 = make_float2(-1.f, -1.f);
 
-    // fp32 screen of two records (see belief_pairs_table_kernel) -> packed records, bit w set when record w needs the exact path
+    // fp32 screen of two records (see belief_pairs_table_kernel) -> packed records; bit w: record w's rounding is inside the
+    // first-level window, bit 4 + w: its inverse-CDF comparison is too close to call
     auto screen_pair = [&](uint32_t seenA, uint32_t seenB, float ufA, float ufB, uint2 rawA, uint2 rawB, uint2& outA, uint2& outB) -> uint32_t {
         const uint32_t rowA = bpt32_s + seenA * (M * 101 * 4), rowB = bpt32_s + seenB * (M * 101 * 4);
         float2 bp[M];
@@ -798,8 +837,9 @@ __global__ void __launch_bounds__(kThreads, 2) belief_pairs_episode_kernel(const
         const float2 win = __fmul2_rn(S, make_float2(kCdfWindow, kCdfWindow));
         const float2 g0 = __ffma2_rn(c0, minus1, uS), g1 = __ffma2_rn(c1, minus1, uS);
         const uint32_t apA = uS.x < c0.x ? 0u : (uS.x < c1.x ? 1u : 2u), apB = uS.y < c0.y ? 0u : (uS.y < c1.y ? 1u : 2u);
-        const bool exA = (dmaxA > kHalfWindow) | (fminf(fabsf(g0.x), fabsf(g1.x)) < win.x) | (ufA > 1.f - 2e-5f);
-        const bool exB = (dmaxB > kHalfWindow) | (fminf(fabsf(g0.y), fabsf(g1.y)) < win.y) | (ufB > 1.f - 2e-5f);
+        const bool rdA = dmaxA > kHalfWindow, rdB = dmaxB > kHalfWindow;          // rounding too close to call (first level)
+        const bool cdA = (fminf(fabsf(g0.x), fabsf(g1.x)) < win.x) | (ufA > 1.f - 2e-5f);
+        const bool cdB = (fminf(fabsf(g0.y), fabsf(g1.y)) < win.y) | (ufB > 1.f - 2e-5f);
         auto pack = [&](bool second, uint32_t ap) -> uint2 {
             uint32_t kb[M];
 #pragma unroll
@@ -813,13 +853,13 @@ __global__ void __launch_bounds__(kThreads, 2) belief_pairs_episode_kernel(const
         };
         outA = pack(false, apA);
         outB = pack(true, apB);
-        return (exA ? 1u : 0u) | (exB ? 2u : 0u);
+        return (rdA ? 1u : 0u) | (rdB ? 2u : 0u) | (cdA ? 16u : 0u) | (cdB ? 32u : 0u);
     };
 
-    // ---- the thread's quads (fixed for the whole episode): quad q = tid + s * 256, s < kEpQuads.  The records live in shared memory
-    // ([slot][thread] 8-byte words: conflict-free), so the quad loop is a real loop (the step body stays inside the instruction
-    // cache) and the exact pass can fix a flagged record in place.
-    const int total = n_envs * KQ;
+    // ---- the lane's quads (fixed for the whole episode): quad slot ql = lane + 32 s of the warp, s < kEpQuads; env = ql / KQ,
+    // quad of the env = ql % KQ.  The records live in shared memory ([slot][thread] 8-byte words: conflict-free), so the quad
+    // loop is a real loop (the step body stays inside the instruction cache) and a flagged record is fixed in place.
+    const int total = n_envs * KQ;                               // quad slots of this warp in use (<= kEpWarpQuads)
     const bool warp_one_env = (KQ & 31) == 0;
     const int prior_k = (int)rint(100.0 / M);
     uint2 prior;
@@ -828,27 +868,28 @@ __global__ void __launch_bounds__(kThreads, 2) belief_pairs_episode_kernel(const
     const uint32_t st_s = (uint32_t)__cvta_generic_to_shared(st_mem) + threadIdx.x * 8u;   // + (4 s + w) * kThreads * 8
 #pragma unroll
     for (int k = 0; k < 4 * kEpQuads; ++k) st_mem[k * kThreads + threadIdx.x] = prior;
-    const int d_el = (int)blockDim.x / KQ, d_sq = (int)blockDim.x % KQ;
-    const int el0 = (int)threadIdx.x / KQ, sq0 = (int)threadIdx.x % KQ;
+    const int d_el = 32 / KQ, d_sq = 32 % KQ;
+    const int el0 = lane / KQ, sq0 = lane % KQ;
     const uint64_t ctr0 = (uint64_t)((P.env_offset + e0) * N + i) * (uint64_t)KQ;
     const uint32_t row_ctr = (uint32_t)N * (uint32_t)KQ;
     // staging of the others' actions of one step (own action skipped, 4 slots per word); requires N % 4 == 0 (checked by the host)
     const int NW = N >> 2, iw = i >> 2;
     const uint32_t sel_mix = (i & 3) == 0 ? 0x4321u : ((i & 3) == 1 ? 0x4320u : ((i & 3) == 2 ? 0x4310u : 0x4210u));
-    // per quad, fixed for the episode: source word offset, byte selector, destination word.  Padding slots (jj >= K) keep
-    // whatever action byte the selector picks — they are computed on but never stored or counted.
+    // per quad, fixed for the episode: source word offset and byte selector.  Padding slots (jj >= K) keep whatever action byte
+    // the selector picks — they are computed on but never stored or counted.
     uint32_t stage_lo[kEpQuads], stage_hi[kEpQuads], stage_src[kEpQuads], stage_sel[kEpQuads];
     {
         int el = el0, sq = sq0;
 #pragma unroll
         for (int s_ = 0; s_ < kEpQuads; ++s_) {
-            const bool ok = (int)threadIdx.x + s_ * (int)blockDim.x < total;
+            const bool ok = lane + 32 * s_ < total;
             stage_src[s_] = ok ? (uint32_t)(el * NW + sq) : 0xFFFFFFFFu;
             stage_sel[s_] = (sq < iw ? 0x3210u : (sq > iw ? 0x4321u : sel_mix)) | (sq + 1 < NW ? 0u : 0x80000000u);   // bit 31: no next word
             el += d_el; sq += d_sq;
             if (sq >= KQ) { sq -= KQ; ++el; }
         }
     }
+    // the actions are written by the kernel before this one: coherent loads (an ld.global.nc may be hoisted above griddepcontrol.wait)
     auto stage_load = [&](int t) {
         const uint32_t* src = reinterpret_cast<const uint32_t*>(P.act + ((int64_t)t * P.E + e0) * N);
 #pragma unroll
@@ -858,12 +899,9 @@ __global__ void __launch_bounds__(kThreads, 2) belief_pairs_episode_kernel(const
             stage_hi[s_] = (ok && !(stage_sel[s_] >> 31)) ? __ldcg(src + stage_src[s_] + 1) : 0u;
         }
     };
-    auto stage_store = [&](int buf) {
+    auto stage_store = [&]() {   // own slots only
 #pragma unroll
-        for (int s_ = 0; s_ < kEpQuads; ++s_) {
-            const int q = (int)threadIdx.x + s_ * (int)blockDim.x;
-            if (q < total) seen4[buf * (EC * KQ) + q] = __byte_perm(stage_lo[s_], stage_hi[s_], stage_sel[s_] & 0xFFFFu);
-        }
+        for (int s_ = 0; s_ < kEpQuads; ++s_) seen4[s_ * kThreads + threadIdx.x] = __byte_perm(stage_lo[s_], stage_hi[s_], stage_sel[s_] & 0xFFFFu);
     };
     auto dump = [&](int64_t trec, uint2 out) {
         if (belief_dump) {
@@ -873,23 +911,19 @@ __global__ void __launch_bounds__(kThreads, 2) belief_pairs_episode_kernel(const
         if (pred_dump) pred_dump[trec] = (uint8_t)(out.y >> 16);
     };
     stage_load(0);
-    stage_store(0);
-    for (int k = threadIdx.x; k < 2 * ECp; k += blockDim.x) counts2[k] = 0u;
-    __syncthreads();
+    stage_store();
+    __syncwarp();
 
     for (int t = 0; t < P.T1; ++t) {
-        const int buf = t & 1;
-        uint32_t* counts = counts2 + buf * ECp;
-        int& queue_n = queue_n2[buf];
         if (t + 1 < P.T1) stage_load(t + 1);                       // next step's actions: in flight during this step's arithmetic
         const uint32_t c2 = ((uint32_t)t & 0xFFFFu) | (kStreamBelief << 16);
         const int64_t tbase = (int64_t)t * P.E * N * K;            // index of step t in the per-step tapes / dumps
         int el = el0, sq = sq0;
 #pragma unroll 1
         for (int s_ = 0; s_ < kEpQuads; ++s_) {
-            const int q = (int)threadIdx.x + s_ * (int)blockDim.x;
-            if (q - lane >= total) break;                          // warp-uniform: whole warp past the end
-            const bool live = q < total;
+            const int ql = lane + 32 * s_;
+            if (32 * s_ >= total) break;                           // warp-uniform: whole warp past the end
+            const bool live = ql < total;
             const int jj0 = 4 * sq;
             const int n_valid = live ? min(4, K - jj0) : 0;
             const int64_t trec0 = tbase + ((e0 + (live ? el : 0)) * N + i) * (int64_t)K + jj0;
@@ -899,7 +933,7 @@ __global__ void __launch_bounds__(kThreads, 2) belief_pairs_episode_kernel(const
                 const uint4 rnd = philox4x32_10_rk(make_uint4((uint32_t)index, (uint32_t)(index >> 32), c2, P.episode), P.rk);
                 words[0] = rnd.x; words[1] = rnd.y; words[2] = rnd.z; words[3] = rnd.w;
             }
-            const uint32_t seen_w = live ? seen4[buf * (EC * KQ) + q] : 0u;
+            const uint32_t seen_w = live ? seen4[s_ * kThreads + threadIdx.x] : 0u;
             const uint32_t sp = st_s + (uint32_t)(4 * s_) * (kThreads * 8u);
             uint2 raw[4];
 #pragma unroll
@@ -914,7 +948,15 @@ __global__ void __launch_bounds__(kThreads, 2) belief_pairs_episode_kernel(const
             uint2 out[4];
             uint32_t need = screen_pair(__byte_perm(seen_w, 0u, 0x4440u), __byte_perm(seen_w, 0u, 0x4441u), uf[0], uf[1], raw[0], raw[1], out[0], out[1]);
             need |= screen_pair(__byte_perm(seen_w, 0u, 0x4442u), __byte_perm(seen_w, 0u, 0x4443u), uf[2], uf[3], raw[2], raw[3], out[2], out[3]) << 2;
-            need &= (1u << n_valid) - 1u;
+            need &= ((1u << n_valid) - 1u) * 0x11u;
+            if (need) {   // ~0.4 % of the quads: second-level test of the rounding flags, value by value
+                uint32_t still = need >> 4;
+#pragma unroll
+                for (int w = 0; w < 4; ++w)
+                    if ((need & ~still) & (1u << w))
+                        still |= belief_refine_rounding<M>(bpt32_s + ((seen_w >> (8 * w)) & 0xFFu) * (M * 101 * 4), raw[w]) ? (1u << w) : 0u;
+                need = still;
+            }
             uint32_t packed = 0u;
 #pragma unroll
             for (int w = 0; w < 4; ++w) {
@@ -924,11 +966,11 @@ __global__ void __launch_bounds__(kThreads, 2) belief_pairs_episode_kernel(const
                     if (belief_dump || pred_dump) dump(trec0 + w, out[w]);
                 }
             }
-            if (need) {   // ~1 % of the quads: the flagged records go to the dense exact pass below, which fixes them in place
-                int pos = atomicAdd(&queue_n, __popc(need));
+            if (need) {   // ~0.1 % of the quads: the flagged records go to the warp's exact pass below, which fixes them in place
+                int pos = atomicAdd(&queue_n_w[warp], __popc(need));
 #pragma unroll
                 for (int w = 0; w < 4; ++w)
-                    if (need & (1u << w)) queue[pos++] = (uint16_t)((q << 2) | w);
+                    if (need & (1u << w)) queue[pos++] = (uint16_t)((ql << 2) | w);
             }
             if (warp_one_env) {
                 const uint32_t sum = __reduce_add_sync(0xffffffffu, packed);
@@ -941,14 +983,13 @@ __global__ void __launch_bounds__(kThreads, 2) belief_pairs_episode_kernel(const
             el += d_el; sq += d_sq;
             if (sq >= KQ) { sq -= KQ; ++el; }
         }
-        __syncthreads();
-        // ---- exact pass: the flagged records, one per thread, with the reference's fp64 sequence, fixed in place
-        const int n_def = queue_n;
-        for (int x = threadIdx.x; x < n_def; x += blockDim.x) {
-            const int code = queue[x], q = code >> 2, w = code & 3;
-            const int el_ = q / KQ, sq_ = q - el_ * KQ;
-            const int owner = q % (int)blockDim.x, s_ = q / (int)blockDim.x;
-            uint2* rp = st_mem + (4 * s_ + w) * kThreads + owner;
+        __syncwarp();
+        // ---- exact pass of the warp: its flagged records, one per lane, with the reference's fp64 sequence, fixed in place
+        const int n_def = *reinterpret_cast<volatile int*>(&queue_n_w[warp]);
+        for (int x = lane; x < n_def; x += 32) {
+            const int code = queue[x], ql = code >> 2, w = code & 3;
+            const int el_ = ql / KQ, sq_ = ql - el_ * KQ;
+            uint2* rp = st_mem + (4 * (ql >> 5) + w) * kThreads + (warp << 5) + (ql & 31);
             const int64_t trec = tbase + ((e0 + el_) * N + i) * (int64_t)K + 4 * sq_ + w;
             double u;
             if (u_injected) {
@@ -958,16 +999,16 @@ __global__ void __launch_bounds__(kThreads, 2) belief_pairs_episode_kernel(const
                 const uint4 rnd = philox4x32_10_rk(make_uint4((uint32_t)index, (uint32_t)(index >> 32), c2, P.episode), P.rk);
                 u = belief_word_to_unit_f64(w == 0 ? rnd.x : (w == 1 ? rnd.y : (w == 2 ? rnd.z : rnd.w)));
             }
-            const uint32_t seen = (seen4[buf * (EC * KQ) + q] >> (8 * w)) & 0xFFu;
+            const uint32_t seen = (seen4[(ql >> 5) * kThreads + (warp << 5) + (ql & 31)] >> (8 * w)) & 0xFFu;
             const uint2 res = belief_exact_record<M>(bpt + seen * (M * 101), fa, *rp, -1, u);
             *rp = res;
             atomicAdd(&counts[el_], 1u << (10u * (res.y >> 16)));
             if (belief_dump || pred_dump) dump(trec, res);
         }
-        if (t + 1 < P.T1) stage_store(buf ^ 1);                    // nobody reads that buffer during this step
-        __syncthreads();
-        // ---- partner mode of step t; this slot of the counters is used again at step t + 2 (two barriers from now)
-        for (int x = threadIdx.x; x < n_envs; x += blockDim.x) {
+        __syncwarp();
+        if (t + 1 < P.T1) stage_store();                           // the exact pass above was the last reader of this step's actions
+        // ---- partner mode of step t
+        for (int x = lane; x < n_envs; x += 32) {
             const uint32_t c = counts[x];
             const int n0 = c & 1023, n1 = (c >> 10) & 1023, n2 = c >> 20;
             int best = 0, bc = n0;
@@ -976,14 +1017,15 @@ __global__ void __launch_bounds__(kThreads, 2) belief_pairs_episode_kernel(const
             P.partner_pred[((int64_t)t * P.E + e0 + x) * N + i] = (uint8_t)best;
             counts[x] = 0u;
         }
-        if (threadIdx.x == blockDim.x - 1) queue_n = 0;              // every thread read it before the barrier above
+        if (lane == 0) queue_n_w[warp] = 0;
+        __syncwarp();
     }
     // ---- the final records
     {
         int el = el0, sq = sq0;
 #pragma unroll
         for (int s_ = 0; s_ < kEpQuads; ++s_) {
-            if ((int)threadIdx.x + s_ * (int)blockDim.x < total) {
+            if (lane + 32 * s_ < total) {
                 uint2* wp = reinterpret_cast<uint2*>(P.records + (((e0 + el) * N + i) * (int64_t)K + 4 * sq) * IA2C_BELIEF_RECORD);
 #pragma unroll
                 for (int w = 0; w < 4; ++w)
@@ -998,11 +1040,12 @@ __global__ void __launch_bounds__(kThreads, 2) belief_pairs_episode_kernel(const
 template <int M>
 int launch_pairs_episode(EpisodePairsArgs& P, cudaStream_t stream) {
     const int KQ = (P.K + 3) / 4;
-    P.envs_per_block = std::max(1, (kEpQuads * kThreads) / KQ);   // <= kEpQuads quads per thread
-    const int64_t env_blocks = (P.E + P.envs_per_block - 1) / P.envs_per_block;
+    P.envs_per_warp = std::max(1, kEpWarpQuads / KQ);              // whole envs per warp, <= kEpQuads quads per lane
+    const int64_t envs_per_block = (int64_t)P.envs_per_warp * kEpWarps;
+    const int64_t env_blocks = (P.E + envs_per_block - 1) / envs_per_block;
     size_t smem = (104 + 3 * M * 101 + M * 3) * sizeof(double) + (((3 * M * 101 + 3) & ~3) + ((2 * M + 3) & ~3)) * sizeof(float) +
-                  (size_t)2 * ((P.envs_per_block + 3) & ~3) * sizeof(uint32_t) + (size_t)4 * kEpQuads * kThreads * (sizeof(uint2) + sizeof(uint16_t)) +
-                  (size_t)2 * P.envs_per_block * KQ * sizeof(uint32_t);
+                  (size_t)kEpWarps * ((P.envs_per_warp + 3) & ~3) * sizeof(uint32_t) +
+                  (size_t)4 * kEpQuads * kThreads * (sizeof(uint2) + sizeof(uint16_t)) + (size_t)kEpQuads * kThreads * sizeof(uint32_t);
     smem = (smem + 15) & ~size_t(15);
     dim3 grid((unsigned)env_blocks, P.N);
     const bool fast = !P.u_injected && !P.belief_dump && !P.pred_dump;
@@ -1090,7 +1133,7 @@ extern "C" int ia2c_belief_update_pairs(uint8_t* records, const double* filter_a
     }
 }
 
-extern "C" int ia2c_belief_supports_episode(int32_t N, int32_t M) { return N >= 33 && N <= 1023 && (N & 3) == 0 && M >= 2 && M <= IA2C_MAX_MODELS; }
+extern "C" int ia2c_belief_supports_episode(int32_t N, int32_t M) { return N >= 33 && N <= 512 && (N & 3) == 0 && M >= 2 && M <= IA2C_MAX_MODELS; }
 
 extern "C" int ia2c_belief_update_pairs_episode(uint8_t* records, const double* filter_action, const uint8_t* act,
                                                 const double* u_injected, uint8_t* pred_dump, uint8_t* belief_dump,
@@ -1098,7 +1141,7 @@ extern "C" int ia2c_belief_update_pairs_episode(uint8_t* records, const double* 
                                                 uint32_t episode, int64_t env_offset, void* stream) {
     IA2C_REQUIRE(E > 0 && T1 > 0 && records && filter_action && act && partner_pred, "ia2c_belief_update_pairs_episode: E=%lld T1=%d or null arrays",
                  (long long)E, T1);
-    IA2C_REQUIRE(ia2c_belief_supports_episode(N, M), "ia2c_belief_update_pairs_episode: needs 33 <= N <= 1023, N %% 4 == 0, 2 <= M <= %d; got N=%d M=%d",
+    IA2C_REQUIRE(ia2c_belief_supports_episode(N, M), "ia2c_belief_update_pairs_episode: needs 33 <= N <= 512, N %% 4 == 0, 2 <= M <= %d; got N=%d M=%d",
                  IA2C_MAX_MODELS, N, M);
     IA2C_REQUIRE(T1 <= 65535, "ia2c_belief_update_pairs_episode: T1=%d", T1);
     EpisodePairsArgs P{records, filter_action, act, u_injected, pred_dump, belief_dump, partner_pred, E, env_offset, N, N - 1, T1, 0, episode, {}};

@@ -36,6 +36,25 @@ constexpr int kRoles = 4;
 constexpr int kBlock = 32 * kRoles;
 constexpr int kRing = 8;
 
+// Diagnostic build (-DIA2C_STAGE_CLOCKS, tools/stage_clocks.py): every stage warp of block 0 sums the cycles it spends between
+// leaving one per-iteration barrier and reaching the next, and prints them next to the loop's total at the end.
+#ifdef IA2C_STAGE_CLOCKS
+__device__ __forceinline__ unsigned long long stage_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define STAGE_CLOCK_ENTRY const unsigned long long sc_entry = stage_ns()
+#define STAGE_CLOCK_WAITED const unsigned long long sc_waited = stage_ns()
+#define STAGE_CLOCK_INIT long long sc_work = 0, sc_t0 = clock64(), sc_start = sc_t0; const unsigned long long sc_loop = stage_ns()
+#define STAGE_SYNC() do { sc_work += clock64() - sc_t0; __syncthreads(); sc_t0 = clock64(); } while (0)
+#define STAGE_CLOCK_REPORT(name) do { if ((blockIdx.x == 0 || blockIdx.x == gridDim.x - 1) && lane == 0) printf("block %3d stage %-6s work %lld of %lld cycles, %d iterations; ns: entry %llu waited +%llu loop +%llu loop end +%llu\n", (int)blockIdx.x, name, sc_work, (long long)(clock64() - sc_start), n_iter, sc_entry % 100000000ull, sc_waited - sc_entry, sc_loop - sc_entry, stage_ns() - sc_entry); } while (0)
+#define STAGE_CLOCK_EXIT(name) do { if ((blockIdx.x == 0 || blockIdx.x == gridDim.x - 1) && lane == 0) printf("block %3d stage %-6s exit +%llu ns\n", (int)blockIdx.x, name, stage_ns() - sc_entry); } while (0)
+#else
+#define STAGE_CLOCK_ENTRY
+#define STAGE_CLOCK_WAITED
+#define STAGE_CLOCK_EXIT(name)
+#define STAGE_CLOCK_INIT
+#define STAGE_SYNC() __syncthreads()
+#define STAGE_CLOCK_REPORT(name)
+#endif
+
 __device__ __forceinline__ uint32_t pack_count(int a) { return a == 0 ? 1u : (a == 1 ? (1u << 10) : (1u << 20)); }
 __device__ __forceinline__ int mode3(int c0, int c1, int c2) {
     int best = 0, bc = c0;
@@ -72,12 +91,14 @@ __global__ void __launch_bounds__(kBlock) rollout_fused_kernel(ia2c_episode_desc
     __shared__ float2 hst_s[4][6][CRITIC ? 32 : 1];      // critic activations (h1 | h2 pairs) of obs[t], slot t & 3
     __shared__ float2 dz1_s[2][3][CRITIC ? 32 : 1];      // dL/dz1 of observation t (backprop warp -> W1-gradient owner), slot t & 1
     __shared__ float4 dy_s[4][CRITIC ? 32 : 1];          // row t's output gradients {jt, dQ[jt], nja, dQ'[nja]}, slot t & 3
+    STAGE_CLOCK_ENTRY;
     pdl_release();
     // constants of the run (k/100, the agents' models): staged while the previous kernel of the stream may still be running
     for (int k = threadIdx.x; k <= 100; k += blockDim.x) tab[k] = __ddiv_rn((double)k, 100.0);
     for (int k = threadIdx.x; k < N * M * A; k += blockDim.x) fa_s[k] = d.filter_action[k];
     __syncthreads();
     pdl_wait();   // parameters (updated by the previous episode's Adam steps) are read only after this
+    STAGE_CLOCK_WAITED;
 
     const int role = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -160,6 +181,7 @@ __global__ void __launch_bounds__(kBlock) rollout_fused_kernel(ia2c_episode_desc
         int32_t* trace_p = d.state_trace ? d.state_trace + e : nullptr;
         double* rew64_p = d.reward_f64 ? d.reward_f64 + e : nullptr;
         const int max_steps = d.max_episode_steps;
+        STAGE_CLOCK_INIT;
         for (int it = 0; it < n_iter; ++it) {
             const int t = it - 1;
             if (t >= 0 && t <= T) {
@@ -227,8 +249,9 @@ __global__ void __launch_bounds__(kBlock) rollout_fused_kernel(ia2c_episode_desc
                 act_p += E * N;
                 ptrue_p += E * N;
             }
-            __syncthreads();
+            STAGE_SYNC();
         }
+        STAGE_CLOCK_REPORT("A");
         if (live && sub == 0) {   // persist the final env state exactly as the per-step path leaves it
             d.env_state[e] = s;
             d.env_hist[e] = hist;
@@ -236,6 +259,7 @@ __global__ void __launch_bounds__(kBlock) rollout_fused_kernel(ia2c_episode_desc
             d.ep_return[e] = ep_ret;
             *reinterpret_cast<uchar2*>(d.env_cls + 2 * e) = make_uchar2((unsigned char)prev_cls, (unsigned char)cur_cls);
         }
+        STAGE_CLOCK_EXIT("A");
     } else if (role == 2) {
         // ================================================================ B: beliefs, step t = it - 2
         const double* fa = fa_s + i * M * A;
@@ -250,6 +274,7 @@ __global__ void __launch_bounds__(kBlock) rollout_fused_kernel(ia2c_episode_desc
         for (int jj = 0; jj < K; ++jj) last_pred[jj] = 0;
         uint8_t* ppred_p = d.partner_pred + e * N + i;
         if (CRITIC) draw_action_init();
+        STAGE_CLOCK_INIT;
         for (int it = 0; it < n_iter; ++it) {
             if (CRITIC) draw_action(it);      // stage R's action half rides on this warp when the critic stages exist
             const int t = it - 2;
@@ -311,8 +336,9 @@ __global__ void __launch_bounds__(kBlock) rollout_fused_kernel(ia2c_episode_desc
                 if (agent) *ppred_p = (uint8_t)pp;
                 ppred_p += E * N;
             }
-            __syncthreads();
+            STAGE_SYNC();
         }
+        STAGE_CLOCK_REPORT("B");
         if (agent) {   // persist the final beliefs exactly as the per-step path leaves them
 #pragma unroll
             for (int jj = 0; jj < K; ++jj) {
@@ -328,9 +354,10 @@ __global__ void __launch_bounds__(kBlock) rollout_fused_kernel(ia2c_episode_desc
     } else if (!CRITIC) {
         // ================================================================ R alone: draws (no critic stage)
         if (role == 3) { draw_action_init(); draw_belief_init(); }
+        STAGE_CLOCK_INIT;
         for (int it = 0; it < n_iter; ++it) {
             if (role == 3) { draw_action(it); draw_belief(it); }
-            __syncthreads();
+            STAGE_SYNC();
         }
     } else {
     // ==================================================================== R + Cf / Cb: draws, critic gradient
@@ -356,6 +383,7 @@ __global__ void __launch_bounds__(kBlock) rollout_fused_kernel(ia2c_episode_desc
 #pragma unroll
             for (int k = 0; k < 3; ++k) { hst_s[slot][k][lane] = a1[k]; hst_s[slot][3 + k][lane] = a2[k]; }
         };
+        STAGE_CLOCK_INIT;
         for (int it = 0; it < n_iter; ++it) {
             const int t = it - 4;
             if (t >= 0 && t < T) {
@@ -397,8 +425,9 @@ __global__ void __launch_bounds__(kBlock) rollout_fused_kernel(ia2c_episode_desc
                 for (int k = 0; k < 3; ++k) dz1[k] = dz1_s[tb & 1][k][lane];
                 accumulate_w1(xb, dz1, gB);
             }
-            __syncthreads();
+            STAGE_SYNC();
         }
+        STAGE_CLOCK_REPORT("Cf");
 #pragma unroll
         for (int k = 0; k < 21; ++k) {
 #pragma unroll
@@ -417,6 +446,7 @@ __global__ void __launch_bounds__(kBlock) rollout_fused_kernel(ia2c_episode_desc
             out[P] = loss;
             if (blockIdx.x == 0 && !(d.flags & IA2C_FLAG_SKIP_ADAM)) d.critic_step[lane] += 1;
         }
+        STAGE_CLOCK_EXIT("Cf");
     } else {
     // ==================================================================== Cb: critic backward, observation t = it - 5
     // ONE backward per observation with both output-gradient contributions it receives (from row t as
@@ -429,6 +459,7 @@ __global__ void __launch_bounds__(kBlock) rollout_fused_kernel(ia2c_episode_desc
 #pragma unroll
     for (int k = 0; k < GA; ++k) gA[k] = make_float2(0.f, 0.f);
     draw_belief_init();
+    STAGE_CLOCK_INIT;
     for (int it = 0; it < n_iter; ++it) {
         draw_belief(it);             // stage R's belief half shares this warp
         const int t = it - 5;
@@ -452,8 +483,9 @@ __global__ void __launch_bounds__(kBlock) rollout_fused_kernel(ia2c_episode_desc
 #pragma unroll
             for (int k = 0; k < 3; ++k) dz1_s[t & 1][k][lane] = dz1[k];
         }
-        __syncthreads();
+        STAGE_SYNC();
     }
+    STAGE_CLOCK_REPORT("R+Cb");
     // reduce over the lanes that own the same agent (lane offsets >= G), then lanes 0..N-1 write one partial row each
 #pragma unroll
     for (int k = 0; k < GA; ++k) {
@@ -470,6 +502,7 @@ __global__ void __launch_bounds__(kBlock) rollout_fused_kernel(ia2c_episode_desc
             if (42 + 2 * k + 1 < P) out[42 + 2 * k + 1] = gA[k].y;
         }
     }
+    STAGE_CLOCK_EXIT("R+Cb");
     }   // Cb
     }   // critic stages
 }
