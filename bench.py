@@ -395,8 +395,9 @@ def kernel_rooflines(torch, _lib, peak_gbs):
                      note="the class API's interface forces 128 B/update of real traffic (likelihood row 24 B, u 8 B, int64 ap 8 B on top of "
                           "the algorithmic 88 B): ncu traffic / algorithmic = 1.31, i.e. 0.95 of HBM by actual bytes"))
     del lik, prev, u, ap, bp
-    # (3) belief update, packed pairwise records (Org-N: 64 agents x 63 modelled others) — K >= 32 dispatches to the table kernel
-    En, N = 2048, 64
+    # (3) belief update, packed pairwise records at the config-5 per-GPU shape (1024 envs x 256 agents x 255 modelled others =
+    #     1.07 GB of records read + written per launch) — K >= 32 dispatches to the table kernel
+    En, N = 1024, 256
     K = N - 1
     rec = torch.zeros(En, N, K, 8, dtype=torch.uint8, device=dev)
     fan = torch.rand(N, 5, 3, dtype=torch.float64, device=dev)
@@ -411,7 +412,7 @@ def kernel_rooflines(torch, _lib, peak_gbs):
                                             En, N, 5, 1, 1, 0, 0, 0, st))
     sec = timeit(pairs)
     pairs_n = En * N * K
-    out.append(entry("belief_pairs_table_kernel<5>", f"{pairs_n} (agent, modelled-other) updates, N=64", 16, 16 * pairs_n, sec,
+    out.append(entry("belief_pairs_table_kernel<5>", f"{pairs_n} (agent, modelled-other) updates, N=256", 16, 16 * pairs_n, sec,
                      pairs_per_s=pairs_n / sec,
                      note="uint8 records (16 B/update instead of the reference layout's 88 B) make this kernel instruction-issue bound, "
                           "not HBM bound (profiles/)"))

@@ -36,24 +36,19 @@ constexpr int kRoles = 4;
 constexpr int kBlock = 32 * kRoles;
 constexpr int kRing = 8;
 
-// Diagnostic build (-DIA2C_STAGE_CLOCKS, tools/stage_clocks.py): every stage warp of block 0 sums the cycles it spends between
-// leaving one per-iteration barrier and reaching the next, and prints them next to the loop's total at the end.
+// Diagnostic build (-DIA2C_STAGE_CLOCKS, tools/stage_clocks.py): the stage warps of the first and the last block of episode 5
+// print when they entered, left griddepcontrol.wait, started / ended the step loop and finished (ns since entry), and the
+// cycles they spent between leaving one per-iteration barrier and reaching the next.
 #ifdef IA2C_STAGE_CLOCKS
-__device__ __forceinline__ unsigned long long stage_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
-#define STAGE_CLOCK_ENTRY const unsigned long long sc_entry = stage_ns()
-#define STAGE_CLOCK_WAITED const unsigned long long sc_waited = stage_ns()
-#define STAGE_CLOCK_INIT long long sc_work = 0, sc_t0 = clock64(), sc_start = sc_t0; const unsigned long long sc_loop = stage_ns()
+#define STAGE_CLOCK_INIT long long sc_work = 0, sc_t0 = clock64(); KCLOCK(sc_loop)
 #define STAGE_SYNC() do { sc_work += clock64() - sc_t0; __syncthreads(); sc_t0 = clock64(); } while (0)
-#define STAGE_CLOCK_REPORT(name) do { if ((blockIdx.x == 0 || blockIdx.x == gridDim.x - 1) && lane == 0) printf("block %3d stage %-6s work %lld of %lld cycles, %d iterations; ns: entry %llu waited +%llu loop +%llu loop end +%llu\n", (int)blockIdx.x, name, sc_work, (long long)(clock64() - sc_start), n_iter, sc_entry % 100000000ull, sc_waited - sc_entry, sc_loop - sc_entry, stage_ns() - sc_entry); } while (0)
-#define STAGE_CLOCK_EXIT(name) do { if ((blockIdx.x == 0 || blockIdx.x == gridDim.x - 1) && lane == 0) printf("block %3d stage %-6s exit +%llu ns\n", (int)blockIdx.x, name, stage_ns() - sc_entry); } while (0)
 #else
-#define STAGE_CLOCK_ENTRY
-#define STAGE_CLOCK_WAITED
-#define STAGE_CLOCK_EXIT(name)
 #define STAGE_CLOCK_INIT
 #define STAGE_SYNC() __syncthreads()
-#define STAGE_CLOCK_REPORT(name)
 #endif
+#define STAGE_CLOCK_EXIT(name) KCLOCK_PRINT(d.episode == 5 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1) && lane == 0, \
+    "rollout block %3d stage %-5s entry %llu: waited +%llu, loop +%llu .. +%llu (work %lld cycles), exit +%llu ns\n", (int)blockIdx.x, name, \
+    sc_entry % 1000000000ull, sc_waited - sc_entry, sc_loop - sc_entry, sc_loop_end - sc_entry, sc_work, stage_ns() - sc_entry)
 
 __device__ __forceinline__ uint32_t pack_count(int a) { return a == 0 ? 1u : (a == 1 ? (1u << 10) : (1u << 20)); }
 __device__ __forceinline__ int mode3(int c0, int c1, int c2) {
@@ -91,14 +86,15 @@ __global__ void __launch_bounds__(kBlock) rollout_fused_kernel(ia2c_episode_desc
     __shared__ float2 hst_s[4][6][CRITIC ? 32 : 1];      // critic activations (h1 | h2 pairs) of obs[t], slot t & 3
     __shared__ float2 dz1_s[2][3][CRITIC ? 32 : 1];      // dL/dz1 of observation t (backprop warp -> W1-gradient owner), slot t & 1
     __shared__ float4 dy_s[4][CRITIC ? 32 : 1];          // row t's output gradients {jt, dQ[jt], nja, dQ'[nja]}, slot t & 3
-    STAGE_CLOCK_ENTRY;
+    __shared__ float red_s[CRITIC ? kCriticP + 1 : 1][33];   // per-lane gradient partials for the block-wide reduction at the end
+    KCLOCK(sc_entry);
     pdl_release();
     // constants of the run (k/100, the agents' models): staged while the previous kernel of the stream may still be running
     for (int k = threadIdx.x; k <= 100; k += blockDim.x) tab[k] = __ddiv_rn((double)k, 100.0);
     for (int k = threadIdx.x; k < N * M * A; k += blockDim.x) fa_s[k] = d.filter_action[k];
     __syncthreads();
     pdl_wait();   // parameters (updated by the previous episode's Adam steps) are read only after this
-    STAGE_CLOCK_WAITED;
+    KCLOCK(sc_waited);
 
     const int role = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -251,7 +247,7 @@ __global__ void __launch_bounds__(kBlock) rollout_fused_kernel(ia2c_episode_desc
             }
             STAGE_SYNC();
         }
-        STAGE_CLOCK_REPORT("A");
+        KCLOCK(sc_loop_end);
         if (live && sub == 0) {   // persist the final env state exactly as the per-step path leaves it
             d.env_state[e] = s;
             d.env_hist[e] = hist;
@@ -338,7 +334,7 @@ __global__ void __launch_bounds__(kBlock) rollout_fused_kernel(ia2c_episode_desc
             }
             STAGE_SYNC();
         }
-        STAGE_CLOCK_REPORT("B");
+        KCLOCK(sc_loop_end);
         if (agent) {   // persist the final beliefs exactly as the per-step path leaves them
 #pragma unroll
             for (int jj = 0; jj < K; ++jj) {
@@ -351,6 +347,7 @@ __global__ void __launch_bounds__(kBlock) rollout_fused_kernel(ia2c_episode_desc
                 *reinterpret_cast<uint2*>(d.belief_records + ((e * N + i) * (int64_t)K + jj) * IA2C_BELIEF_RECORD) = make_uint2(lo, hi);
             }
         }
+        STAGE_CLOCK_EXIT("B");
     } else if (!CRITIC) {
         // ================================================================ R alone: draws (no critic stage)
         if (role == 3) { draw_action_init(); draw_belief_init(); }
@@ -363,7 +360,6 @@ __global__ void __launch_bounds__(kBlock) rollout_fused_kernel(ia2c_episode_desc
     // ==================================================================== R + Cf / Cb: draws, critic gradient
     constexpr int P = kCriticP, GN = F2<J>::G2;          // 148 floats = 74 float2 (147 gradient entries + the loss)
     const float inv_b = agent ? 1.f / (float)((int64_t)T * d.E_total) : 0.f;   // dead lanes contribute nothing
-    float* out = partials + ((int64_t)(lane < N ? lane : 0) * gridDim.x + blockIdx.x) * (P + 1);
 
     if (role == 0) {
         // ================================================================ Cf: critic forward + TD error, row t = it - 4
@@ -427,25 +423,12 @@ __global__ void __launch_bounds__(kBlock) rollout_fused_kernel(ia2c_episode_desc
             }
             STAGE_SYNC();
         }
-        STAGE_CLOCK_REPORT("Cf");
+        KCLOCK(sc_loop_end);
+        // hand the lane's partial sums to the block-wide reduction at the end of the kernel
 #pragma unroll
-        for (int k = 0; k < 21; ++k) {
-#pragma unroll
-            for (int off = 16; off >= G; off >>= 1) {
-                gB[k].x += __shfl_xor_sync(0xffffffffu, gB[k].x, off);
-                gB[k].y += __shfl_xor_sync(0xffffffffu, gB[k].y, off);
-            }
-        }
-        if (lane < N) {
-#pragma unroll
-            for (int k = 0; k < 21; ++k) { out[2 * k] = gB[k].x; out[2 * k + 1] = gB[k].y; }
-        }
-#pragma unroll
-        for (int off = 16; off >= G; off >>= 1) loss += __shfl_xor_sync(0xffffffffu, loss, off);
-        if (lane < N) {
-            out[P] = loss;
-            if (blockIdx.x == 0 && !(d.flags & IA2C_FLAG_SKIP_ADAM)) d.critic_step[lane] += 1;
-        }
+        for (int k = 0; k < 21; ++k) { red_s[2 * k][lane] = gB[k].x; red_s[2 * k + 1][lane] = gB[k].y; }
+        red_s[P][lane] = loss;
+        if (lane < N && blockIdx.x == 0 && !(d.flags & IA2C_FLAG_SKIP_ADAM)) d.critic_step[lane] += 1;
         STAGE_CLOCK_EXIT("Cf");
     } else {
     // ==================================================================== Cb: critic backward, observation t = it - 5
@@ -485,26 +468,30 @@ __global__ void __launch_bounds__(kBlock) rollout_fused_kernel(ia2c_episode_desc
         }
         STAGE_SYNC();
     }
-    STAGE_CLOCK_REPORT("R+Cb");
-    // reduce over the lanes that own the same agent (lane offsets >= G), then lanes 0..N-1 write one partial row each
+    KCLOCK(sc_loop_end);
 #pragma unroll
     for (int k = 0; k < GA; ++k) {
-#pragma unroll
-        for (int off = 16; off >= G; off >>= 1) {
-            gA[k].x += __shfl_xor_sync(0xffffffffu, gA[k].x, off);
-            gA[k].y += __shfl_xor_sync(0xffffffffu, gA[k].y, off);
-        }
-    }
-    if (lane < N) {
-#pragma unroll
-        for (int k = 0; k < GA; ++k) {
-            if (42 + 2 * k < P) out[42 + 2 * k] = gA[k].x;
-            if (42 + 2 * k + 1 < P) out[42 + 2 * k + 1] = gA[k].y;
-        }
+        if (42 + 2 * k < P) red_s[42 + 2 * k][lane] = gA[k].x;
+        if (42 + 2 * k + 1 < P) red_s[42 + 2 * k + 1][lane] = gA[k].y;
     }
     STAGE_CLOCK_EXIT("R+Cb");
     }   // Cb
     }   // critic stages
+    if (CRITIC) {
+        // Block-wide reduction of the 147 gradient entries + the loss over the lanes that own the same agent (lane = env * G +
+        // agent): every thread sums a few (entry, agent) items over the block's envs in ascending order and writes them to the
+        // agent's partial row of this block.  (One shared-memory pass instead of log2(32 / G) shuffle rounds over 148 registers
+        // in two warps: 1200 SHFL + FADD per block and ~2 us at the end of every rollout.)
+        __syncthreads();
+        constexpr int P1 = kCriticP + 1;
+        for (int item = threadIdx.x; item < P1 * N; item += kBlock) {
+            const int entry = item / N, a = item - entry * N;
+            float sum = red_s[entry][a];
+#pragma unroll
+            for (int j = 1; j < EPW; ++j) sum += red_s[entry][a + G * j];
+            partials[((int64_t)a * gridDim.x + blockIdx.x) * P1 + entry] = sum;
+        }
+    }
 }
 
 template <int N, int M>

@@ -379,12 +379,15 @@ __global__ void __launch_bounds__(kGradThreads) actor_grad_kernel(ia2c_episode_d
     __shared__ __align__(16) float wc[SmemNet<J>::size];
     __shared__ __align__(16) float w[SmemNet<A>::size];
     __shared__ float red[(kGradThreads / 32) * (P + 1)];
+    KCLOCK(k_entry);
     pdl_prologue();
+    KCLOCK(k_waited);
     const int n = blockIdx.y, N = d.N;
     stage_smemnet<J>(wc, d.critic_params + (int64_t)n * PC);
     stage_smemnet<A>(w, d.actor_params + (int64_t)n * P);
     if (blockIdx.x == 0 && threadIdx.x == 0 && !(d.flags & IA2C_FLAG_SKIP_ADAM)) d.actor_step[n] += 1;
     __syncthreads();
+    KCLOCK(k_staged);
     const int64_t E = d.E, rows = (int64_t)d.T * E;
     const ChunkPlan cp = chunk_plan(d.T, E, N);
     const int64_t items = E * cp.n_chunks;
@@ -469,10 +472,14 @@ __global__ void __launch_bounds__(kGradThreads) actor_grad_kernel(ia2c_episode_d
             cur = nxt;
         }
     }
+    KCLOCK(k_loop_end);
     float g[2 * GN];
     unpack_g2(g2, g);
     g[P] = loss;
     block_reduce_store<P + 1>(reinterpret_cast<float(&)[P + 1]>(g), red, partials + ((int64_t)n * gridDim.x + blockIdx.x) * (P + 1));
+    KCLOCK_PRINT(d.episode == 5 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1) && blockIdx.y == 0 && threadIdx.x == 0,
+                 "actor_grad block %3d entry %llu: waited +%llu, staged +%llu, rows done +%llu, exit +%llu ns\n", (int)blockIdx.x,
+                 k_entry % 1000000000ull, k_waited - k_entry, k_staged - k_entry, k_loop_end - k_entry, stage_ns() - k_entry);
 }
 
 // Sum partials over blocks (fixed order) -> grad[n][0..P] (slot P = loss); optionally Adam.  (reduce.cuh holds
@@ -481,7 +488,9 @@ __global__ void __launch_bounds__(kGradThreads) actor_grad_kernel(ia2c_episode_d
 // The partials are L2-resident, so a thread's chain of dependent adds costs one L2 round trip per term: many
 // short slices (<= 8 terms at 256 partial blocks, loads issued back to back) instead of few long ones.
 __global__ void __launch_bounds__(32 * kReduceSlices) reduce_adam_kernel(ReduceArgs R) {
+    KCLOCK(k_entry);
     pdl_prologue();
+    KCLOCK(k_waited);
     const int n = blockIdx.x, P = R.P;
     const int col = threadIdx.x & 31, slice = threadIdx.x >> 5;
     const int i = blockIdx.y * 32 + col;
@@ -513,6 +522,8 @@ __global__ void __launch_bounds__(32 * kReduceSlices) reduce_adam_kernel(ReduceA
 #pragma unroll
     for (int k = 1; k < kReduceSlices; ++k) s += part[k][col];
     finish_entry(R, n, i, s, bias);
+    KCLOCK_PRINT(blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0, "reduce_adam P=%d entry %llu: waited +%llu, exit +%llu ns\n", P,
+                 k_entry % 1000000000ull, k_waited - k_entry, stage_ns() - k_entry);
 }
 
 __global__ void bump_steps_kernel(int32_t* step, int n) {
