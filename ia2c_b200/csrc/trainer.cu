@@ -43,6 +43,12 @@ namespace {
 constexpr int F = IA2C_OBS_FEATURES, A = IA2C_AGENT_ACTIONS, J = IA2C_JOINT_ACTIONS;
 constexpr int kRolloutThreads = 128;
 constexpr int kGradThreads = 128;
+#ifdef IA2C_STAGE_CLOCKS
+// diagnostic build only: stamps of the update kernels of the LAST episode (0-3 critic reduce / exchange: left the wait, local
+// reduction done, all ranks' words in, block 0 done; 4-7 actor gradient: entry, left the wait, rows done, block 0 done;
+// 10-13 actor reduce / exchange).  Read back with ia2c_debug_kclocks.
+__device__ unsigned long long g_kclock[16];
+#endif
 constexpr float kEpsClamp = 1.1920928955078125e-07f;
 
 __device__ __forceinline__ int mode3(int c0, int c1, int c2) {
@@ -380,8 +386,10 @@ __global__ void __launch_bounds__(kGradThreads) actor_grad_kernel(ia2c_episode_d
     __shared__ __align__(16) float w[SmemNet<A>::size];
     __shared__ float red[(kGradThreads / 32) * (P + 1)];
     KCLOCK(k_entry);
+    KSTAMP(g_kclock, 4);
     pdl_prologue();
     KCLOCK(k_waited);
+    KSTAMP(g_kclock, 5);
     const int n = blockIdx.y, N = d.N;
     stage_smemnet<J>(wc, d.critic_params + (int64_t)n * PC);
     stage_smemnet<A>(w, d.actor_params + (int64_t)n * P);
@@ -473,10 +481,12 @@ __global__ void __launch_bounds__(kGradThreads) actor_grad_kernel(ia2c_episode_d
         }
     }
     KCLOCK(k_loop_end);
+    KSTAMP(g_kclock, 6);
     float g[2 * GN];
     unpack_g2(g2, g);
     g[P] = loss;
     block_reduce_store<P + 1>(reinterpret_cast<float(&)[P + 1]>(g), red, partials + ((int64_t)n * gridDim.x + blockIdx.x) * (P + 1));
+    KSTAMP(g_kclock, 7);
     KCLOCK_PRINT(d.episode == 5 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1) && blockIdx.y == 0 && threadIdx.x == 0,
                  "actor_grad block %3d entry %llu: waited +%llu, staged +%llu, rows done +%llu, exit +%llu ns\n", (int)blockIdx.x,
                  k_entry % 1000000000ull, k_waited - k_entry, k_staged - k_entry, k_loop_end - k_entry, stage_ns() - k_entry);
@@ -488,9 +498,8 @@ __global__ void __launch_bounds__(kGradThreads) actor_grad_kernel(ia2c_episode_d
 // The partials are L2-resident, so a thread's chain of dependent adds costs one L2 round trip per term: many
 // short slices (<= 8 terms at 256 partial blocks, loads issued back to back) instead of few long ones.
 __global__ void __launch_bounds__(32 * kReduceSlices) reduce_adam_kernel(ReduceArgs R) {
-    KCLOCK(k_entry);
     pdl_prologue();
-    KCLOCK(k_waited);
+    KSTAMP(g_kclock, R.P == kCriticP ? 0 : 10);
     const int n = blockIdx.x, P = R.P;
     const int col = threadIdx.x & 31, slice = threadIdx.x >> 5;
     const int i = blockIdx.y * 32 + col;
@@ -522,8 +531,7 @@ __global__ void __launch_bounds__(32 * kReduceSlices) reduce_adam_kernel(ReduceA
 #pragma unroll
     for (int k = 1; k < kReduceSlices; ++k) s += part[k][col];
     finish_entry(R, n, i, s, bias);
-    KCLOCK_PRINT(blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0, "reduce_adam P=%d entry %llu: waited +%llu, exit +%llu ns\n", P,
-                 k_entry % 1000000000ull, k_waited - k_entry, stage_ns() - k_entry);
+    KSTAMP(g_kclock, R.P == kCriticP ? 3 : 13);
 }
 
 __global__ void bump_steps_kernel(int32_t* step, int n) {
@@ -683,9 +691,9 @@ static int run_reduce(const ia2c_episode_desc* d, int which, int from_partials, 
 // host's next check (trainer.py: check_comm — before statistics, checkpoints and after bench regions).
 struct PeerArgs {
     int rank, world;
-    unsigned long long* inbox[8];   // 64-bit words {epoch << 32 | float bits}
+    unsigned long long* inbox[IA2C_MAX_RANKS];   // 64-bit words {epoch << 32 | float bits}
     unsigned long long* mc_inbox;   // multicast mapping or null
-    int32_t* error[8];
+    int32_t* error[IA2C_MAX_RANKS];
     uint32_t epoch;
     int t;                          // Adam step number of this update (host-tracked in the multi-rank path)
     int64_t stride;                 // words per (parity, rank) slot = N * (kCriticP + 1)
@@ -716,6 +724,7 @@ __global__ void __launch_bounds__(32 * kReduceSlices) allreduce_adam_kernel(Redu
     pdl_release();
     if (threadIdx.x == blockDim.x - 1) bias = adam_bias(X.t, R.lr);   // from launch arguments only: overlaps the predecessor's tail
     pdl_wait();
+    KSTAMP(g_kclock, R.P == kCriticP ? 0 : 10);
     if (X.error[X.rank] && *reinterpret_cast<volatile int32_t*>(X.error[X.rank]) != 0) return;   // a previous exchange failed: no-op
     const int P = R.P, col = threadIdx.x & 31, slice = threadIdx.x >> 5;
     const int parity = (int)(X.epoch & 1u);
@@ -737,6 +746,7 @@ __global__ void __launch_bounds__(32 * kReduceSlices) allreduce_adam_kernel(Redu
         }
         part[slice][col] = s;
         __syncthreads();
+        KSTAMP(g_kclock, R.P == kCriticP ? 1 : 11);
         float g = 0.f;
         int late = 0;
         const bool owner = slice == 0 && i <= P;
@@ -752,24 +762,30 @@ __global__ void __launch_bounds__(32 * kReduceSlices) allreduce_adam_kernel(Redu
             } else {
                 for (int p = 0; p < X.world; ++p) st_word_sys(X.inbox[p] + mine, word);      // NVLink stores (self included)
             }
+            // first look at every rank's word at once (independent loads: one L2 round trip instead of `world` in a row), then
+            // wait, in rank order, only for the ones that have not arrived
+            const unsigned long long* w0 = X.inbox[X.rank] + (int64_t)parity * X.world * X.stride + idx;
+            unsigned long long m[IA2C_MAX_RANKS];
+#pragma unroll
+            for (int r = 0; r < IA2C_MAX_RANKS; ++r) m[r] = r < X.world ? ld_word_sys(w0 + (int64_t)r * X.stride) : 0ull;
             unsigned long long t_start = 0;
-            for (int r = 0; r < X.world; ++r) {                              // rank order: identical sums on every rank
-                const unsigned long long* w = X.inbox[X.rank] + ((int64_t)parity * X.world + r) * X.stride + idx;
-                unsigned long long m = ld_word_sys(w);
+#pragma unroll
+            for (int r = 0; r < IA2C_MAX_RANKS; ++r) {                       // rank order: identical sums on every rank
+                if (r >= X.world || late) continue;
                 int spins = 0;
-                while ((uint32_t)(m >> 32) != X.epoch) {
+                while ((uint32_t)(m[r] >> 32) != X.epoch) {
                     __nanosleep(32);
                     if ((++spins & 63) == 0) {                               // wall-clock budget, checked every 64 polls
                         const unsigned long long now = global_ns();
                         if (t_start == 0) t_start = now;
                         else if (now - t_start > X.timeout_ns) { late = 1; break; }
                     }
-                    m = ld_word_sys(w);
+                    m[r] = ld_word_sys(w0 + (int64_t)r * X.stride);
                 }
-                if (late) break;
-                g += __uint_as_float((uint32_t)m);
+                if (!late) g += __uint_as_float((uint32_t)m[r]);
             }
         }
+        KSTAMP(g_kclock, R.P == kCriticP ? 2 : 12);
         if (__syncthreads_or(late)) {      // block-uniform: nothing of this chunk is applied, the block stops
             if (threadIdx.x == 0)
                 for (int p = 0; p < X.world; ++p)
@@ -790,6 +806,7 @@ __global__ void __launch_bounds__(32 * kReduceSlices) allreduce_adam_kernel(Redu
                 adam_update(R.params[k], R.m[k], R.v[k], g, bias);
             }
         }
+        KSTAMP(g_kclock, R.P == kCriticP ? 3 : 13);
     }
 }
 
@@ -1148,3 +1165,9 @@ extern "C" int ia2c_allreduce_adam(const ia2c_episode_desc* d, int32_t which, co
     const int grid = std::min(total, kSMs);          // persistent: every block is resident
     return launch_pdl("allreduce_adam_kernel", allreduce_adam_kernel, dim3(grid), dim3(32 * kReduceSlices), 0, s, R, X, total, chunks_per_agent);
 }
+
+#ifdef IA2C_STAGE_CLOCKS
+extern "C" int ia2c_debug_kclocks(unsigned long long* out16) {
+    return cudaMemcpyFromSymbol(out16, ia2c::g_kclock, sizeof(unsigned long long) * 16) == cudaSuccess ? 0 : -1;
+}
+#endif

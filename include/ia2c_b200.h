@@ -283,6 +283,7 @@ int ia2c_critic_phase(const ia2c_episode_desc* d, void* stream);
 int ia2c_actor_phase(const ia2c_episode_desc* d, void* stream);
 /* Adam from the gradient buffers (after a multi-GPU all-reduce): which = 0 critics, 1 actors. */
 int ia2c_apply_adam(const ia2c_episode_desc* d, int32_t which, void* stream);
+#define IA2C_MAX_RANKS 8   /* one node: NVLink peers of an 8-GPU box */
 /* Multi-GPU: fused gradient all-reduce + Adam over NVLink peer memory, ONE kernel per optimiser phase instead of
  * reduce -> NCCL all-reduce -> Adam.  Run it after the phase's gradient kernel (ia2c_rollout with
  * IA2C_FLAG_FUSED_CRITIC, or ia2c_critic_phase / ia2c_actor_phase with IA2C_FLAG_GRAD_ONLY).
@@ -299,9 +300,9 @@ int ia2c_apply_adam(const ia2c_episode_desc* d, int32_t which, void* stream);
  * poll its own error word (trainer.py: check_comm) before trusting or checkpointing parameters. */
 typedef struct ia2c_peer_desc {
     int32_t rank, world;       /* world <= 8 (one NVSwitch domain) */
-    uint64_t* inbox[8];
+    uint64_t* inbox[IA2C_MAX_RANKS];
     uint64_t* mc_inbox;        /* multicast (NVLS) mapping of the inboxes, or NULL */
-    int32_t* error[8];         /* every rank's error word; error[rank] is this rank's own */
+    int32_t* error[IA2C_MAX_RANKS];         /* every rank's error word; error[rank] is this rank's own */
     uint32_t timeout_us;       /* poll budget per entry in microseconds (0 -> 2 000 000) */
     uint32_t reserved;
 } ia2c_peer_desc;

@@ -1,27 +1,12 @@
 #!/usr/bin/env python
-"""Where a headline episode's kernels spend their time (needs a library built with -DIA2C_STAGE_CLOCKS: `python
-tools/stage_clocks.py --build` writes var_tmp/libclk.so; run with IA2C_B200_LIB=var_tmp/libclk.so).  The first / last block of
-the rollout (each stage warp), of the actor-gradient kernel and of the reduce + Adam kernels print %globaltimer stamps."""
+"""tools/stage_clocks.py for a multi-rank run (torchrun, one rank per GPU): the fused all-reduce + Adam kernel of every rank
+prints when it entered, left its wait, finished its local reduction and had every rank's words (diagnostic build only)."""
 import os
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-if "--build" in sys.argv:
-    import subprocess
-    from ia2c_b200 import build as B
-    B.build()
-    out = os.path.join(B.ROOT, "var_tmp")
-    os.makedirs(out, exist_ok=True)
-    objs = []
-    for src in B.SOURCES:
-        obj = os.path.join(out, src.replace(".cu", ".o"))
-        subprocess.run([B.NVCC, *B.FLAGS, "-DIA2C_STAGE_CLOCKS", "-diag-suppress", "177", "-c", os.path.join(B.CSRC, src), "-o", obj], check=True)
-        objs.append(obj)
-    subprocess.run([B.NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", os.path.join(out, "libclk.so"), *objs, "-lcudart"], check=True)
-    for o in objs:
-        os.remove(o)
-    sys.exit(0)
 import torch
+import torch.distributed as dist
 
 from ia2c_b200.trainer import IA2CTrainer, reference_init
 
@@ -44,8 +29,18 @@ def report_update_stamps(tag=""):
     print(f"{tag}critic exchange left its wait -> actor exchange done: {us(0, 13):.2f} us")
 
 
-tr = IA2CTrainer(4096, n_agents=2, init=reference_init(2, 5, seed=0), seed=1)
-for _ in range(7):   # the kernels print during episode 5
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+tr = IA2CTrainer(4096 * world, n_agents=2, init=reference_init(2, 5, seed=0), seed=1, rank=rank, world_size=world)
+for _ in range(12):
     tr.train_episode()
 torch.cuda.synchronize()
-report_update_stamps()
+tr.check_comm()
+for r in range(world):
+    dist.barrier()
+    if r == rank:
+        report_update_stamps(f"rank {rank}: ")
+        sys.stdout.flush()
+dist.barrier()
+dist.destroy_process_group()
