@@ -719,7 +719,7 @@ int launch_pairs_table(PairsArgs& P, cudaStream_t stream) {
 // During a rollout nothing reads a belief before the update phase: the env and the actors depend on the sampled actions
 // only (ia2c.py:72-102 — the filter's predicted action enters the critic's index at ia2c.py:104-121, after the episode).
 // The rollout therefore runs its T+1 env / actor steps first and then updates every belief record through ALL T+1 steps in
-// ONE kernel with the record resident in registers: the 16 bytes per update that belief_pairs_table_kernel streams per step
+// ONE kernel with the record resident on the SM (shared memory): the 16 bytes per update that belief_pairs_table_kernel streams per step
 // (8-byte record read + written) shrink to one 8-byte store per EPISODE, and the byte unpack / pack, the address arithmetic,
 // the cp.async ring and the table build are paid once per record-episode instead of once per update.  Same screen, same
 // exact sequence, same Philox counters as the per-step kernel: bit-identical records, predictions and partner modes
