@@ -376,7 +376,7 @@ def kernel_rooflines(torch, _lib, peak_gbs):
     sec = timeit(env_step)
     out.append(entry("org_step_thread_kernel", f"{E} env-steps (N=2)", 54, 54 * E, sec))
     del env, act
-    # (1b) Org-N env step, warp per env with the agents in lanes (N=256 per-agent uint8 actions: 52 + N bytes per env-step)
+    # (1b) Org-N env step, a warp per 32 envs with the agents' action bytes in lanes (N=256 uint8 actions: 52 + N bytes per env-step)
     Ew, Nw = 1 << 21, 256
     env = OrgVecEnv(Ew, n_agents=Nw)
     act = torch.randint(0, 3, (Ew, Nw), dtype=torch.uint8, device=dev)
@@ -385,7 +385,7 @@ def kernel_rooflines(torch, _lib, peak_gbs):
         _lib.check(lib.ia2c_org_step_agents(_lib.ptr(env.state), _lib.ptr(env.hist), _lib.ptr(env.cls), None, _lib.ptr(act),
                                             _lib.ptr(env.obs), None, _lib.ptr(env.reward_f32), None, None, Ew, Nw, 0, st))
     sec = timeit(env_step_warp)
-    out.append(entry("org_step_warp_kernel", f"{Ew} env-steps (N=256, Org-N)", 52 + Nw, (52 + Nw) * Ew, sec))
+    out.append(entry("org_step_warp32_kernel", f"{Ew} env-steps (N=256, Org-N)", 52 + Nw, (52 + Nw) * Ew, sec))
     del env, act
     # (2) belief update, dense reference layout (fp64 [R,5] in/out)
     R = 1 << 23

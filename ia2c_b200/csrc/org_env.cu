@@ -137,7 +137,80 @@ org_step_thread_kernel(OrgArrays A, const int32_t* __restrict__ joint, const uin
     store_obs_warp(A.obs_out, e - (threadIdx.x & 31), E, prev_cls, cur_cls, active, stage[threadIdx.x >> 5]);
 }
 
-// One warp per env, agents in lanes (N > 8).  Counts are packed 3 x 10 bits and reduced by shuffles.
+// Counts of the action codes 0 / 1 / 2 among the four bytes of a word, packed 3 x 10 bits; any other byte counts nothing.
+__device__ __forceinline__ uint32_t count_actions4(uint32_t v) {
+    const uint32_t hi = (v >> 2) & 0x3F3F3F3Fu;                                    // the six high bits of every byte
+    const uint32_t ok = ~((((hi + 0x7F7F7F7Fu) | hi) & 0x80808080u) >> 7) & 0x01010101u;   // 1 where the byte is < 4
+    const uint32_t b0 = v, b1 = v >> 1;
+    return (uint32_t)__popc(~b0 & ~b1 & ok) | ((uint32_t)__popc(b0 & ~b1 & ok) << 10) | ((uint32_t)__popc(~b0 & b1 & ok) << 20);
+}
+
+// Org-N step for N > 8: a warp owns 32 envs.  Phase 1 counts the actions of one env (or of several, for N <= 64) per load
+// instruction with the agents' bytes in the lanes — 32-bit words, 4 actions each, counts packed 3 x 10 bits, one warp
+// reduction per env — and hands env j's total to lane j.  Phase 2 is org_step_thread_kernel's body with all 32 lanes busy:
+// coalesced state / reward-history loads and stores, observation rows staged through shared memory into 128-bit stores.
+// (The first version spent a whole warp per env and left the transition to lane 0: 0.8 TB/s at N = 256.)
+// Requires N % 4 == 0 (rows are then word-aligned); other N take org_step_warp_kernel below.
+template <int WPL>   // words per lane and env: >= ceil(N / 128), a power of two; 1 also covers the several-envs-per-load case
+__global__ void __launch_bounds__(kThreads)
+org_step_warp32_kernel(OrgArrays A, const uint8_t* __restrict__ actions, int N, int64_t E) {
+    __shared__ float stage[kThreads / 32][192];
+    const int lane = threadIdx.x & 31;
+    const int64_t e0 = ((int64_t)blockIdx.x * kThreads + threadIdx.x - lane);   // the warp's first env
+    if (e0 >= E) return;
+    const int NW = N >> 2;                                   // words per env
+    const uint32_t* a4 = reinterpret_cast<const uint32_t*>(actions);
+    uint32_t mine = 0;                                       // lane j: packed counts of env e0 + j
+    if (WPL == 1 && NW <= 16) {
+        // several envs per load instruction: a group of GW = pow2 >= NW lanes per env
+        int GW = 1;
+        while (GW < NW) GW <<= 1;
+        const int EPI = 32 / GW, g = lane / GW, w = lane % GW;
+        for (int it = 0; it < GW; ++it) {                    // 32 / EPI iterations
+            const int64_t e = e0 + it * EPI + g;
+            uint32_t packed = (w < NW && e < E) ? count_actions4(a4[e * NW + w]) : 0u;
+            for (int off = GW >> 1; off > 0; off >>= 1) packed += __shfl_xor_sync(0xffffffffu, packed, off);
+            const uint32_t got = __shfl_sync(0xffffffffu, packed, ((lane - it * EPI) & (EPI - 1)) * GW);
+            if (lane >= it * EPI && lane < (it + 1) * EPI) mine = got;
+        }
+    } else {
+        // one env per warp reduction; WPL words per lane and env, EPC envs (8 loads per lane) in flight
+        constexpr int EPC = WPL >= 8 ? 1 : 8 / WPL;
+        for (int j0 = 0; j0 < 32; j0 += EPC) {
+            uint32_t v[EPC][WPL];
+#pragma unroll
+            for (int u = 0; u < EPC; ++u) {
+                const int64_t e = e0 + j0 + u;
+#pragma unroll
+                for (int k = 0; k < WPL; ++k) {
+                    const int w = lane + 32 * k;
+                    v[u][k] = (w < NW && e < E) ? a4[e * NW + w] : 0xFFFFFFFFu;   // 0xFF bytes count nothing
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < EPC; ++u) {
+                uint32_t packed = 0u;
+#pragma unroll
+                for (int k = 0; k < WPL; ++k) packed += count_actions4(v[u][k]);
+                const uint32_t total = __reduce_add_sync(0xffffffffu, packed);
+                if (lane == j0 + u) mine = total;
+            }
+        }
+    }
+    const int64_t e = e0 + lane;
+    const bool active = e < E;
+    int prev_cls = 1, cur_cls = 1;
+    if (active) {
+        const int s = A.state[e];
+        int s2;
+        double base;
+        org_transition(s, mine & 1023, (mine >> 10) & 1023, (mine >> 20) & 1023, N, s2, base);
+        org_finish(A, e, s, s2, base, true, prev_cls, cur_cls);
+    }
+    store_obs_warp(A.obs_out, e0, E, prev_cls, cur_cls, active, stage[threadIdx.x >> 5]);
+}
+
+// One warp per env, agents in lanes: the general form (any N > 8, unaligned rows).  Counts are packed 3 x 10 bits and reduced by shuffles.
 __global__ void __launch_bounds__(kThreads)
 org_step_warp_kernel(OrgArrays A, const uint8_t* __restrict__ actions, int N, int64_t E) {
     const int lane = threadIdx.x & 31;
@@ -213,6 +286,15 @@ extern "C" int ia2c_org_step_agents(int32_t* state, double* hist, uint8_t* cls, 
     if (N <= 8) {
         org_step_thread_kernel<false><<<ceil_div(E, kThreads), kThreads, 0, as_stream(stream)>>>(A, nullptr, actions, N, E);
         return check_launch("org_step_thread_kernel<agents>");
+    }
+    if ((N & 3) == 0 && (reinterpret_cast<uintptr_t>(actions) & 3) == 0) {
+        const dim3 grid((unsigned)ceil_div(E, kThreads));
+        const cudaStream_t s = as_stream(stream);
+        if (N <= 128) org_step_warp32_kernel<1><<<grid, kThreads, 0, s>>>(A, actions, N, E);
+        else if (N <= 256) org_step_warp32_kernel<2><<<grid, kThreads, 0, s>>>(A, actions, N, E);
+        else if (N <= 512) org_step_warp32_kernel<4><<<grid, kThreads, 0, s>>>(A, actions, N, E);
+        else org_step_warp32_kernel<8><<<grid, kThreads, 0, s>>>(A, actions, N, E);
+        return check_launch("org_step_warp32_kernel");
     }
     org_step_warp_kernel<<<ceil_div(E * 32, kThreads), kThreads, 0, as_stream(stream)>>>(A, actions, N, E);
     return check_launch("org_step_warp_kernel");

@@ -64,8 +64,9 @@ def test_walk_vec_env_and_drop_in_class(golden):
     o, rr, *_ = single.step(torch.tensor(8))
 
 
-@pytest.mark.parametrize("E", [1, 31, 33, 1000, 4096])
-@pytest.mark.parametrize("N", [2, 3, 8, 9, 33, 64, 256])
+@pytest.mark.parametrize("E,N", [(e, n) for e in (1, 31, 33, 1000, 4096) for n in (2, 3, 8, 9, 33, 64, 256)] +
+                         # the 32-envs-per-warp kernel (N % 4 == 0): several envs per load (N <= 64), masked tail words, 1 / 2 / 4 / 8 words per lane
+                         [(e, n) for e in (1, 33, 1000) for n in (12, 36, 100, 128, 260, 516, 1020)])
 def test_org_n_matches_oracle(E, N):
     import torch
     from ia2c_b200.org_env import OrgVecEnv
