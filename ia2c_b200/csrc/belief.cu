@@ -714,7 +714,7 @@ int launch_pairs_table(PairsArgs& P, cudaStream_t stream) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Whole-episode pairwise update for many modelled others (K >= 32): the trainer's rollout.
+// Whole-episode pairwise update for many modelled others (12 <= N <= 512, N % 4 == 0): the trainer's rollout.
 //
 // During a rollout nothing reads a belief before the update phase: the env and the actors depend on the sampled actions
 // only (ia2c.py:72-102 — the filter's predicted action enters the critic's index at ia2c.py:104-121, after the episode).
@@ -1133,7 +1133,7 @@ extern "C" int ia2c_belief_update_pairs(uint8_t* records, const double* filter_a
     }
 }
 
-extern "C" int ia2c_belief_supports_episode(int32_t N, int32_t M) { return N >= 33 && N <= 512 && (N & 3) == 0 && M >= 2 && M <= IA2C_MAX_MODELS; }
+extern "C" int ia2c_belief_supports_episode(int32_t N, int32_t M) { return N >= 12 && N <= 512 && (N & 3) == 0 && M >= 2 && M <= IA2C_MAX_MODELS; }
 
 extern "C" int ia2c_belief_update_pairs_episode(uint8_t* records, const double* filter_action, const uint8_t* act,
                                                 const double* u_injected, uint8_t* pred_dump, uint8_t* belief_dump,
@@ -1141,7 +1141,7 @@ extern "C" int ia2c_belief_update_pairs_episode(uint8_t* records, const double* 
                                                 uint32_t episode, int64_t env_offset, void* stream) {
     IA2C_REQUIRE(E > 0 && T1 > 0 && records && filter_action && act && partner_pred, "ia2c_belief_update_pairs_episode: E=%lld T1=%d or null arrays",
                  (long long)E, T1);
-    IA2C_REQUIRE(ia2c_belief_supports_episode(N, M), "ia2c_belief_update_pairs_episode: needs 33 <= N <= 512, N %% 4 == 0, 2 <= M <= %d; got N=%d M=%d",
+    IA2C_REQUIRE(ia2c_belief_supports_episode(N, M), "ia2c_belief_update_pairs_episode: needs 12 <= N <= 512, N %% 4 == 0, 2 <= M <= %d; got N=%d M=%d",
                  IA2C_MAX_MODELS, N, M);
     IA2C_REQUIRE(T1 <= 65535, "ia2c_belief_update_pairs_episode: T1=%d", T1);
     EpisodePairsArgs P{records, filter_action, act, u_injected, pred_dump, belief_dump, partner_pred, E, env_offset, N, N - 1, T1, 0, episode, {}};

@@ -610,10 +610,20 @@ extern "C" int ia2c_rollout(const ia2c_episode_desc* d, void* stream) {
     if (episode_beliefs && !(d->flags & IA2C_FLAG_ROLLOUT_PER_STEP) && d->N <= 256) {
         // ONE persistent kernel for the T+1 env / actor steps, then ONE kernel for the episode's belief updates
         const int threads = ((d->N + 31) / 32) * 32;
-        int epb = (int)std::min<int64_t>(kManyMaxEnvs, std::max<int64_t>(1, (d->E + 2 * kSMs - 1) / (2 * kSMs)));
-        epb = std::min(epb, threads);            // one owner thread per env of the chunk
-        const int64_t grid = (d->E + epb - 1) / epb;
         const size_t smem = (size_t)kManyMaxEnvs * (8 + 1 + 1) * 4 + (size_t)kManyMaxEnvs * threads;
+        // envs per block: a block walks its envs one after the other, so an episode costs (waves of resident blocks) x (envs per
+        // block) — take the split that minimises it (1024 x 256: 7 envs = one wave of 147 blocks instead of two waves of 4)
+        static int resident_per_sm[9] = {0};     // by threads / 32; the same on every B200 of the box
+        int& per_sm = resident_per_sm[threads / 32];
+        if (per_sm == 0 && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rollout_many_kernel, threads, smem) != cudaSuccess) per_sm = 1;
+        const int64_t resident = (int64_t)kSMs * std::max(1, per_sm);
+        int epb = 1;
+        int64_t best = INT64_MAX;
+        for (int c = 1; c <= std::min(kManyMaxEnvs, threads); ++c) {   // one owner thread per env of the chunk
+            const int64_t blocks = (d->E + c - 1) / c, cost = ((blocks + resident - 1) / resident) * c;
+            if (cost <= best) { best = cost; epb = c; }   // ties: the larger chunk (fewer blocks, weights loaded once per more envs)
+        }
+        const int64_t grid = (d->E + epb - 1) / epb;
         if (int rc = launch_pdl("rollout_many_kernel", rollout_many_kernel, dim3((unsigned)grid), dim3(threads), smem, s, *d, epb)) return rc;
         return ia2c_belief_update_pairs_episode(d->belief_records, d->filter_action, d->act, d->inj_u_belief, d->pred_dump, d->belief_dump,
                                                 d->partner_pred, d->E, d->N, d->M, d->T + 1, d->seed, d->episode, d->env_offset, stream);
