@@ -714,7 +714,7 @@ int launch_pairs_table(PairsArgs& P, cudaStream_t stream) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Whole-episode pairwise update for many modelled others (12 <= N <= 512, N % 4 == 0): the trainer's rollout.
+// Whole-episode pairwise update for many modelled others (9 <= N <= 512): the trainer's rollout.
 //
 // During a rollout nothing reads a belief before the update phase: the env and the actors depend on the sampled actions
 // only (ia2c.py:72-102 — the filter's predicted action enters the critic's index at ia2c.py:104-121, after the episode).
@@ -872,36 +872,62 @@ __global__ void __launch_bounds__(kThreads, 2) belief_pairs_episode_kernel(const
     const int el0 = lane / KQ, sq0 = lane % KQ;
     const uint64_t ctr0 = (uint64_t)((P.env_offset + e0) * N + i) * (uint64_t)KQ;
     const uint32_t row_ctr = (uint32_t)N * (uint32_t)KQ;
-    // staging of the others' actions of one step (own action skipped, 4 slots per word); requires N % 4 == 0 (checked by the host)
+    // staging of the others' actions of one step (own action skipped, 4 slots per word).  N % 4 == 0: every env's row of actions
+    // is word-aligned — one or two 32-bit loads per quad and a byte permutation that drops the own action; any other N: four
+    // byte loads per quad.
+    const bool aligned = (N & 3) == 0;
     const int NW = N >> 2, iw = i >> 2;
     const uint32_t sel_mix = (i & 3) == 0 ? 0x4321u : ((i & 3) == 1 ? 0x4320u : ((i & 3) == 2 ? 0x4310u : 0x4210u));
-    // per quad, fixed for the episode: source word offset and byte selector.  Padding slots (jj >= K) keep whatever action byte
-    // the selector picks — they are computed on but never stored or counted.
+    // per quad, fixed for the episode — aligned: source word offset and byte selector; otherwise: byte offset of the env's row
+    // and the quad's first slot.  Padding slots (jj >= K) keep whatever the selector picks / zero — they are computed on but
+    // never stored or counted.
     uint32_t stage_lo[kEpQuads], stage_hi[kEpQuads], stage_src[kEpQuads], stage_sel[kEpQuads];
     {
         int el = el0, sq = sq0;
 #pragma unroll
         for (int s_ = 0; s_ < kEpQuads; ++s_) {
             const bool ok = lane + 32 * s_ < total;
-            stage_src[s_] = ok ? (uint32_t)(el * NW + sq) : 0xFFFFFFFFu;
-            stage_sel[s_] = (sq < iw ? 0x3210u : (sq > iw ? 0x4321u : sel_mix)) | (sq + 1 < NW ? 0u : 0x80000000u);   // bit 31: no next word
+            if (aligned) {
+                stage_src[s_] = ok ? (uint32_t)(el * NW + sq) : 0xFFFFFFFFu;
+                stage_sel[s_] = (sq < iw ? 0x3210u : (sq > iw ? 0x4321u : sel_mix)) | (sq + 1 < NW ? 0u : 0x80000000u);   // bit 31: no next word
+            } else {
+                stage_src[s_] = ok ? (uint32_t)(el * N) : 0xFFFFFFFFu;
+                stage_sel[s_] = (uint32_t)(4 * sq);
+            }
             el += d_el; sq += d_sq;
             if (sq >= KQ) { sq -= KQ; ++el; }
         }
     }
     // the actions are written by the kernel before this one: coherent loads (an ld.global.nc may be hoisted above griddepcontrol.wait)
     auto stage_load = [&](int t) {
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(P.act + ((int64_t)t * P.E + e0) * N);
+        const uint8_t* src8 = P.act + ((int64_t)t * P.E + e0) * N;
+        if (aligned) {
+            const uint32_t* src = reinterpret_cast<const uint32_t*>(src8);
 #pragma unroll
-        for (int s_ = 0; s_ < kEpQuads; ++s_) {
-            const bool ok = stage_src[s_] != 0xFFFFFFFFu;
-            stage_lo[s_] = ok ? __ldcg(src + stage_src[s_]) : 0u;
-            stage_hi[s_] = (ok && !(stage_sel[s_] >> 31)) ? __ldcg(src + stage_src[s_] + 1) : 0u;
+            for (int s_ = 0; s_ < kEpQuads; ++s_) {
+                const bool ok = stage_src[s_] != 0xFFFFFFFFu;
+                stage_lo[s_] = ok ? __ldcg(src + stage_src[s_]) : 0u;
+                stage_hi[s_] = (ok && !(stage_sel[s_] >> 31)) ? __ldcg(src + stage_src[s_] + 1) : 0u;
+            }
+        } else {
+#pragma unroll
+            for (int s_ = 0; s_ < kEpQuads; ++s_) {
+                uint32_t word = 0u;
+                if (stage_src[s_] != 0xFFFFFFFFu) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int jj = (int)stage_sel[s_] + k;               // modelled-other slot -> agent index, skipping self
+                        if (jj < K) word |= (uint32_t)__ldcg(src8 + stage_src[s_] + jj + (jj >= i ? 1 : 0)) << (8 * k);
+                    }
+                }
+                stage_lo[s_] = word;
+            }
         }
     };
     auto stage_store = [&]() {   // own slots only
 #pragma unroll
-        for (int s_ = 0; s_ < kEpQuads; ++s_) seen4[s_ * kThreads + threadIdx.x] = __byte_perm(stage_lo[s_], stage_hi[s_], stage_sel[s_] & 0xFFFFu);
+        for (int s_ = 0; s_ < kEpQuads; ++s_)
+            seen4[s_ * kThreads + threadIdx.x] = aligned ? __byte_perm(stage_lo[s_], stage_hi[s_], stage_sel[s_] & 0xFFFFu) : stage_lo[s_];
     };
     auto dump = [&](int64_t trec, uint2 out) {
         if (belief_dump) {
@@ -1133,7 +1159,7 @@ extern "C" int ia2c_belief_update_pairs(uint8_t* records, const double* filter_a
     }
 }
 
-extern "C" int ia2c_belief_supports_episode(int32_t N, int32_t M) { return N >= 12 && N <= 512 && (N & 3) == 0 && M >= 2 && M <= IA2C_MAX_MODELS; }
+extern "C" int ia2c_belief_supports_episode(int32_t N, int32_t M) { return N >= 9 && N <= 512 && M >= 2 && M <= IA2C_MAX_MODELS; }
 
 extern "C" int ia2c_belief_update_pairs_episode(uint8_t* records, const double* filter_action, const uint8_t* act,
                                                 const double* u_injected, uint8_t* pred_dump, uint8_t* belief_dump,
@@ -1141,7 +1167,7 @@ extern "C" int ia2c_belief_update_pairs_episode(uint8_t* records, const double* 
                                                 uint32_t episode, int64_t env_offset, void* stream) {
     IA2C_REQUIRE(E > 0 && T1 > 0 && records && filter_action && act && partner_pred, "ia2c_belief_update_pairs_episode: E=%lld T1=%d or null arrays",
                  (long long)E, T1);
-    IA2C_REQUIRE(ia2c_belief_supports_episode(N, M), "ia2c_belief_update_pairs_episode: needs 12 <= N <= 512, N %% 4 == 0, 2 <= M <= %d; got N=%d M=%d",
+    IA2C_REQUIRE(ia2c_belief_supports_episode(N, M), "ia2c_belief_update_pairs_episode: needs 9 <= N <= 512, 2 <= M <= %d; got N=%d M=%d",
                  IA2C_MAX_MODELS, N, M);
     IA2C_REQUIRE(T1 <= 65535, "ia2c_belief_update_pairs_episode: T1=%d", T1);
     EpisodePairsArgs P{records, filter_action, act, u_injected, pred_dump, belief_dump, partner_pred, E, env_offset, N, N - 1, T1, 0, episode, {}};

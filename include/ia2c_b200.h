@@ -106,7 +106,7 @@ int ia2c_belief_update_pairs(uint8_t* records, const double* filter_action, cons
  * and outputs are the trajectory arrays.  Bit-identical to T1 calls of ia2c_belief_update_pairs (reset_prior at the first).
  *   act uint8[T1,E,N]; u_injected double[T1,E,N,K] or NULL -> Philox(seed, episode, t, ...);
  *   pred_dump uint8[T1,E,N,K], belief_dump uint8[T1,E,N,K,M] (may be NULL); partner_pred uint8[T1,E,N] out;
- *   records uint8[E,N,K,8] out.  Requires ia2c_belief_supports_episode(N, M): 12 <= N <= 512, N % 4 == 0. */
+ *   records uint8[E,N,K,8] out.  Requires ia2c_belief_supports_episode(N, M): 9 <= N <= 512. */
 int ia2c_belief_supports_episode(int32_t N, int32_t M);
 int ia2c_belief_update_pairs_episode(uint8_t* records, const double* filter_action, const uint8_t* act, const double* u_injected,
                                      uint8_t* pred_dump, uint8_t* belief_dump, uint8_t* partner_pred, int64_t E, int32_t N,
