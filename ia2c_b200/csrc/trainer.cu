@@ -759,12 +759,19 @@ __global__ void __launch_bounds__(32 * kReduceSlices) allreduce_adam_kernel(Redu
         KSTAMP(g_kclock, R.P == kCriticP ? 1 : 11);
         float g = 0.f;
         int late = 0;
-        const bool owner = slice == 0 && i <= P;
+        // Warp 0 owns the chunk's 32 entries (poll, sum in rank order, Adam); warp 1 computes the same local sums (same order:
+        // bit-identical) and PUSHES them, then waits for the remote stores to be acknowledged (fence.sys) while warp 0 is already
+        // polling.  Without that the acknowledgements were collected at grid completion and the next kernel left its
+        // griddepcontrol.wait 2-3 us later than after a kernel without peer stores (profiles/r02_timeline.md).
+        const bool owner = slice == 0 && i <= P, pusher = slice == 1 && i <= P;
         const int64_t idx = (int64_t)n * (P + 1) + i;
-        if (owner) {
+        if (owner || pusher) {
+            s = part[0][col];
 #pragma unroll
             for (int k = 1; k < kReduceSlices; ++k) s += part[k][col];
             if (i == P) s *= R.loss_scale;
+        }
+        if (pusher) {
             const int64_t mine = ((int64_t)parity * X.world + X.rank) * X.stride + idx;
             const unsigned long long word = ((unsigned long long)X.epoch << 32) | (unsigned long long)__float_as_uint(s);
             if (X.mc_inbox) {
@@ -772,6 +779,9 @@ __global__ void __launch_bounds__(32 * kReduceSlices) allreduce_adam_kernel(Redu
             } else {
                 for (int p = 0; p < X.world; ++p) st_word_sys(X.inbox[p] + mine, word);      // NVLink stores (self included)
             }
+            __threadfence_system();
+        }
+        if (owner) {
             // first look at every rank's word at once (independent loads: one L2 round trip instead of `world` in a row), then
             // wait, in rank order, only for the ones that have not arrived
             const unsigned long long* w0 = X.inbox[X.rank] + (int64_t)parity * X.world * X.stride + idx;
