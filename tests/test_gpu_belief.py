@@ -77,14 +77,16 @@ def _pairs_oracle(fa, act, prior, u):
     K = N - 1
     ap = np.zeros((E, N, K), dtype=np.int64)
     bp = np.zeros_like(prior)
-    for i in range(N):
-        for jj, j in enumerate(others_of(i, N)):
-            a, b, _ = B.belief_update(fa[i], B.likelihood_from_action(act[:, j], 3), prior[:, i, jj], u[:, i, jj])
-            ap[:, i, jj], bp[:, i, jj] = a, b
+    M = prior.shape[-1]
+    for i in range(N):   # one oracle call per agent: its K modelled others x E envs are independent rows sharing the agent's models
+        others = np.asarray(list(others_of(i, N)))
+        a, b, _ = B.belief_update(fa[i], B.likelihood_from_action(act[:, others].reshape(-1), 3), prior[:, i].reshape(-1, M), u[:, i].reshape(-1))
+        ap[:, i], bp[:, i] = a.reshape(E, K), b.reshape(E, K, M)
     return ap, bp
 
 
-@pytest.mark.parametrize("E,N,M", [(1, 2, 5), (37, 2, 5), (300, 3, 5), (9, 5, 3), (5, 64, 5), (2, 256, 5), (3, 7, 6), (4, 6, 2), (3, 65, 5), (70, 33, 5), (40, 130, 5)])
+@pytest.mark.parametrize("E,N,M", [(1, 2, 5), (37, 2, 5), (300, 3, 5), (9, 5, 3), (5, 64, 5), (2, 256, 5), (3, 7, 6), (4, 6, 2), (3, 65, 5), (70, 33, 5), (40, 130, 5),
+                                   (2, 600, 5), (1, 1023, 3)])   # N > 512: only the per-step kernel exists
 def test_pairs_kernel_vs_oracle(E, N, M):
     import torch
     from ia2c_b200 import _lib

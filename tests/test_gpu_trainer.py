@@ -297,7 +297,7 @@ def test_full_size_properties(E, N):
     assert a["env_state"].min() >= 0 and a["env_state"].max() <= 4
 
 
-@pytest.mark.parametrize("E,N,T", [(6, 64, 7), (3, 132, 4), (700, 36, 6), (41, 256, 3), (130, 12, 5), (64, 16, 30), (9, 32, 4), (5, 65, 4), (40, 10, 6), (3, 130, 3)])
+@pytest.mark.parametrize("E,N,T", [(6, 64, 7), (3, 132, 4), (700, 36, 6), (41, 256, 3), (130, 12, 5), (64, 16, 30), (9, 32, 4), (5, 65, 4), (40, 10, 6), (3, 130, 3), (2, 300, 3)])
 def test_whole_episode_belief_kernel_equals_the_per_step_rollout(E, N, T):
     """N > 8 rollout: env / actor steps first and ONE belief kernel for the whole episode (default where the library supports it)
     against one belief kernel per step (belief_kernel="step"): every rollout output byte and every update output bit."""
