@@ -172,7 +172,7 @@ def ref_runner(*argv, timeout=900):
 
 def cpu_baseline_legs(n_envs):
     """cpu_baseline for our arm's line (rank 0, N=1): the reference's own loops, bounded to ~20-30 s of CPU work."""
-    out, err = ref_runner("all", "--envs", n_envs, "--warmup", 1, "--episodes", 3, "--warm-envs", 64)
+    out, err = ref_runner("all", "--envs", n_envs, "--warmup", 1, "--episodes", 6, "--warm-envs", 64)
     if out is None:
         r = cpu_port_rate(2, 2048, min_seconds=10.0)
         return {"value": r["value"], "unit": UNIT, "cores": r["blas_threads"], "kind": "port",
