@@ -248,6 +248,16 @@ def test_pipelined_host_episodes_match_sequential_calls(n):
     assert np.array_equal(host(a.ep_return), piped[-1]["ep_return"]) and np.array_equal(host(a.loss_out)[0], piped[-1]["critic_loss"])
     wa, wb = a.window_stats(), b.window_stats()
     assert np.array_equal(wa["critic_loss_window"], wb["critic_loss_window"]) and wa["mean_return"] == wb["mean_return"]
+    # a second call: the same list again (pointer array served from the cache) with NEW contents in the first tape, then a
+    # different list of the same length — both must keep matching the sequential path
+    ua[0].copy_(torch.from_numpy(rng.rand(T + 1, E, N).astype(np.float32)))
+    tapes = [a.pack_host_tape(x, y) for x, y in zip(ua, ub)]
+    for tape_list, xs, ys in ((tapes, ua, ub), (tapes, ua, ub), (tapes[::-1], ua[::-1], ub[::-1])):
+        piped = a.train_episodes_host(tape_list)
+        seq = [b.train_episode_host(x, y) for x, y in zip(xs, ys)]
+        for p, q in zip(piped, seq):
+            assert np.array_equal(p["ep_return"], q["ep_return"]) and np.array_equal(p["actor_loss"], q["actor_loss"])
+    assert np.array_equal(host(a.actor_params), host(b.actor_params))
 
 
 @pytest.mark.parametrize("fused", [False, True])
